@@ -1,0 +1,320 @@
+"""ctypes binding of ``libdeepmod_b200.so`` (the C ABI in ``include/deepmod_b200.h``).
+
+There is no CPU implementation behind these calls: if the shared object is missing
+or no B200 is visible, loading / ``Context`` construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdeepmod_b200.so")
+
+FP32, BF16 = 0, 1
+READ_OK, READ_MISMATCH, READ_BAD_ALIGN, READ_LESS_EVENT = 0, 1, 2, 3
+STATUS_TEXT = {READ_OK: "", READ_MISMATCH: "Error Does not match",      # myDetect.py:870
+               READ_BAD_ALIGN: "Error alignment/event count mismatch",
+               READ_LESS_EVENT: "Less Event"}                           # myDetect.py:704
+WINDOW, FNUM, HIDDEN = 21, 7, 100
+TC_DUMP_BYTES = 137216
+
+_fp = C.POINTER(C.c_float)
+_i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int32)
+_u8p = C.POINTER(C.c_uint8)
+_i8p = C.POINTER(C.c_int8)
+
+
+class DmWeights(C.Structure):
+    _fields_ = [("kernel", (_fp * 3) * 2), ("bias", (_fp * 3) * 2), ("cls_w", _fp), ("cls_b", _fp)]
+
+
+class DmBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32),
+                ("ev_off", _i64p), ("ev_mean", _fp), ("ev_stdv", _fp), ("ev_len", _fp), ("ev_base", _u8p),
+                ("col_off", _i64p), ("col_refbase", _u8p), ("col_readbase", _u8p), ("col_refpos", _i64p),
+                ("start_clip", _i32p), ("end_clip", _i32p), ("contig", _i32p), ("strand", _i8p)]
+
+
+class DeepModError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# name -> (restype, argtypes); must list every function include/deepmod_b200.h declares
+SIGNATURES = {
+    "dm_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(DmWeights), C.c_int]),
+    "dm_destroy": (None, [C.c_void_p]),
+    "dm_last_error": (C.c_char_p, [C.c_void_p]),
+    "dm_version": (C.c_int, []),
+    "dm_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "dm_forward_windows": (C.c_int, [C.c_void_p, C.c_int64, _fp, _fp, _u8p]),
+    "dm_set_genome": (C.c_int, [C.c_void_p, C.c_int32, _i64p, C.c_char]),
+    "dm_hist_clear": (C.c_int, [C.c_void_p]),
+    "dm_hist_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _i64p]),
+    "dm_hist_nonzero": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _i64p, _i32p, _i32p, _i64p]),
+    "dm_write_bed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_char_p, C.c_char_p, _i64p]),
+    "dm_detect_batch": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _fp, _u8p, _i32p]),
+    "dm_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _i64p]),
+    "dm_detect_resident": (C.c_int, [C.c_void_p, C.c_int]),
+    "dm_fetch_results": (C.c_int, [C.c_void_p, _fp, _u8p, _i32p]),
+    "dm_build_windows": (C.c_int, [C.c_void_p, _fp]),
+    "dm_launch_count": (C.c_int64, [C.c_void_p]),
+    "dm_last_timing": (C.c_int, [C.c_void_p, _fp, _fp]),
+    "dm_selftest_umma": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _fp]),
+    "dm_debug_tc_windows": (C.c_int, [C.c_void_p, C.c_int64, _fp, C.c_int, _u8p, C.c_int64, _fp]),
+}
+
+
+def load_library(path=None):
+    """dlopen the CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.isfile(p):
+        raise DeepModError("%s is missing: build it with `python -m deepmod_b200.build` "
+                           "(deepmod_b200 has no CPU fallback)" % p)
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype)) if a is not None else None
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class PackedBatch(object):
+    """Host-side packed read batch (see ``deepmod_b200.synth`` for the field meanings).
+
+    Holds contiguous, correctly typed numpy arrays and the ``DmBatch`` struct pointing at them.
+    """
+    FIELDS = (("ev_off", np.int64), ("ev_mean", np.float32), ("ev_stdv", np.float32), ("ev_len", np.float32),
+              ("ev_base", np.uint8), ("col_off", np.int64), ("col_refbase", np.uint8), ("col_readbase", np.uint8),
+              ("col_refpos", np.int64), ("start_clip", np.int32), ("end_clip", np.int32), ("contig", np.int32),
+              ("strand", np.int8))
+
+    def __init__(self, batch):
+        self.a = {}
+        for k, dt in self.FIELDS:
+            v = batch.get(k)
+            if v is None:
+                if k != "ev_base":
+                    raise ValueError("packed batch lacks %r" % k)
+                self.a[k] = None
+            else:
+                self.a[k] = _arr(v, dt)
+        n = len(self.a["start_clip"])
+        for k in ("end_clip", "contig", "strand"):
+            if len(self.a[k]) != n:
+                raise ValueError("per-read arrays disagree on the number of reads")
+        if len(self.a["ev_off"]) != n + 1 or len(self.a["col_off"]) != n + 1:
+            raise ValueError("offset arrays must have n_reads+1 entries")
+        ne = int(self.a["ev_off"][-1]) if n else 0
+        nc = int(self.a["col_off"][-1]) if n else 0
+        for k in ("ev_mean", "ev_stdv", "ev_len", "ev_base"):
+            if self.a[k] is not None and len(self.a[k]) != ne:
+                raise ValueError("%s has %d entries, offsets say %d" % (k, len(self.a[k]), ne))
+        for k in ("col_refbase", "col_readbase", "col_refpos"):
+            if len(self.a[k]) != nc:
+                raise ValueError("%s has %d entries, offsets say %d" % (k, len(self.a[k]), nc))
+        self.n_reads = n
+        lmap = np.diff(self.a["ev_off"]) - self.a["start_clip"] - self.a["end_clip"]
+        self.n_windows_per_read = np.where(lmap >= 50, lmap, 0).astype(np.int64)   # myDetect.py:702
+        self.n_windows = int(self.n_windows_per_read.sum())
+        s = DmBatch()
+        s.n_reads = n
+        ct = {np.int64: C.c_int64, np.float32: C.c_float, np.uint8: C.c_uint8, np.int32: C.c_int32, np.int8: C.c_int8}
+        for k, dt in self.FIELDS:
+            setattr(s, k, _ptr(self.a[k], ct[dt]))
+        self.struct = s
+
+    def nbytes(self):
+        return sum(v.nbytes for v in self.a.values() if v is not None)
+
+
+class Context(object):
+    """One GPU context (``dm_ctx``): weights resident, one stream, one accumulator."""
+
+    def __init__(self, model, device=0, precision=FP32):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        self._keep = []
+        w = DmWeights()
+        for d in range(2):
+            for l in range(3):
+                k = _arr(model.kernel[d][l], np.float32)
+                b = _arr(model.bias[d][l], np.float32)
+                self._keep += [k, b]
+                w.kernel[d][l] = _ptr(k, C.c_float)
+                w.bias[d][l] = _ptr(b, C.c_float)
+        cw, cb = _arr(model.cls_w, np.float32), _arr(model.cls_b, np.float32)
+        self._keep += [cw, cb]
+        w.cls_w, w.cls_b = _ptr(cw, C.c_float), _ptr(cb, C.c_float)
+        rc = self.lib.dm_create(C.byref(self._h), int(device), C.byref(w), int(precision))
+        if rc != 0:
+            msg = self.lib.dm_last_error(None)
+            self._h = C.c_void_p()
+            raise DeepModError("dm_create failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        self.device = device
+        self.precision = precision
+        self.contig_len = None
+        self.base = None
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.dm_last_error(self._h)
+            raise DeepModError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+    def close(self):
+        if self._h:
+            self.lib.dm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_precision(self, precision):
+        self._check(self.lib.dm_set_precision(self._h, int(precision)), "dm_set_precision")
+        self.precision = precision
+
+    @property
+    def launches(self):
+        return int(self.lib.dm_launch_count(self._h))
+
+    def last_timing(self):
+        a, b = C.c_float(), C.c_float()
+        self._check(self.lib.dm_last_timing(self._h, C.byref(a), C.byref(b)), "dm_last_timing")
+        return a.value, b.value
+
+    # -- model only (the session seam, myDetect.py:816-820) ----------------------------------
+    def forward_windows(self, X):
+        X = _arr(X, np.float32)
+        if X.ndim != 3 or X.shape[1:] != (WINDOW, FNUM):
+            raise ValueError("X must be [n,%d,%d]" % (WINDOW, FNUM))
+        n = X.shape[0]
+        p1 = np.zeros(n, np.float32)
+        pred = np.zeros(n, np.uint8)
+        self._check(self.lib.dm_forward_windows(self._h, n, _ptr(X, C.c_float), _ptr(p1, C.c_float), _ptr(pred, C.c_uint8)),
+                    "dm_forward_windows")
+        return p1, pred
+
+    # -- accumulator -------------------------------------------------------------------------
+    def set_genome(self, contig_len, base):
+        cl = _arr(contig_len, np.int64)
+        self._check(self.lib.dm_set_genome(self._h, len(cl), _ptr(cl, C.c_int64), base.encode()[0:1]), "dm_set_genome")
+        self.contig_len = cl
+        self.base = base
+
+    def hist_clear(self):
+        self._check(self.lib.dm_hist_clear(self._h), "dm_hist_clear")
+
+    def hist_device_ptr(self):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self.lib.dm_hist_device_ptr(self._h, C.byref(p), C.byref(n)), "dm_hist_device_ptr")
+        return p.value, n.value
+
+    def hist_tensor(self):
+        """The accumulator as a torch int64 CUDA tensor aliasing the library's memory (for the
+        one NCCL sum at the end of a multi-GPU job; uint64 lanes add the same as int64)."""
+        import torch
+        ptr, n = self.hist_device_ptr()
+
+        class _Alias(object):
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3,
+                                        "strides": None}
+        return torch.as_tensor(_Alias(), device=torch.device("cuda", self.device))
+
+    def hist_nonzero(self, contig, strand):
+        n = C.c_int64()
+        s = 1 if strand in (1, "+") else -1
+        self._check(self.lib.dm_hist_nonzero(self._h, contig, s, 0, None, None, None, C.byref(n)), "dm_hist_nonzero")
+        k = n.value
+        pos, cov, mod = np.zeros(k, np.int64), np.zeros(k, np.int32), np.zeros(k, np.int32)
+        if k:
+            self._check(self.lib.dm_hist_nonzero(self._h, contig, s, k, _ptr(pos, C.c_int64), _ptr(cov, C.c_int32),
+                                                 _ptr(mod, C.c_int32), C.byref(n)), "dm_hist_nonzero")
+        return pos, cov, mod
+
+    def write_bed(self, contig, strand, chrom, path):
+        n = C.c_int64()
+        s = 1 if strand in (1, "+") else -1
+        self._check(self.lib.dm_write_bed(self._h, contig, s, chrom.encode(), path.encode(), C.byref(n)), "dm_write_bed")
+        return n.value
+
+    # -- the hot path ------------------------------------------------------------------------
+    def detect_batch(self, batch, want_p1=True, want_pred=True, out=None):
+        """get_Feature + mPredict1 + reducer for a packed batch with host buffers.
+        ``out`` may hold preallocated (pinned) ``p1``/``pred``/``status`` arrays."""
+        pb = batch if isinstance(batch, PackedBatch) else PackedBatch(batch)
+        out = out or {}
+        p1 = out.get("p1") if want_p1 else None
+        pred = out.get("pred") if want_pred else None
+        if want_p1 and p1 is None:
+            p1 = np.zeros(pb.n_windows, np.float32)
+        if want_pred and pred is None:
+            pred = np.zeros(pb.n_windows, np.uint8)
+        status = out.get("status")
+        if status is None:
+            status = np.zeros(pb.n_reads, np.int32)
+        self._check(self.lib.dm_detect_batch(self._h, C.byref(pb.struct), _ptr(p1, C.c_float), _ptr(pred, C.c_uint8),
+                                             _ptr(status, C.c_int32)), "dm_detect_batch")
+        return p1, pred, status
+
+    def upload(self, batch):
+        pb = batch if isinstance(batch, PackedBatch) else PackedBatch(batch)
+        n = C.c_int64()
+        self._check(self.lib.dm_batch_upload(self._h, C.byref(pb.struct), C.byref(n)), "dm_batch_upload")
+        self._resident = pb
+        return n.value
+
+    def detect_resident(self, accumulate=True):
+        self._check(self.lib.dm_detect_resident(self._h, 1 if accumulate else 0), "dm_detect_resident")
+
+    def fetch(self, n_windows, n_reads):
+        p1, pred, status = np.zeros(n_windows, np.float32), np.zeros(n_windows, np.uint8), np.zeros(n_reads, np.int32)
+        self._check(self.lib.dm_fetch_results(self._h, _ptr(p1, C.c_float), _ptr(pred, C.c_uint8), _ptr(status, C.c_int32)),
+                    "dm_fetch_results")
+        return p1, pred, status
+
+    def build_windows(self, n_windows):
+        out = np.zeros((n_windows, WINDOW, FNUM), np.float32)
+        if n_windows:
+            self._check(self.lib.dm_build_windows(self._h, _ptr(out, C.c_float)), "dm_build_windows")
+        return out
+
+    # -- instrumentation -----------------------------------------------------------------------
+    def selftest_umma(self, n, k):
+        err = C.c_float()
+        self._check(self.lib.dm_selftest_umma(self._h, n, k, C.byref(err)), "dm_selftest_umma")
+        return err.value
+
+    def debug_tc_windows(self, X, max_steps):
+        X = _arr(X, np.float32)
+        n = X.shape[0]
+        dump = np.zeros(TC_DUMP_BYTES, np.uint8)
+        p1 = np.zeros(n, np.float32)
+        self._check(self.lib.dm_debug_tc_windows(self._h, n, _ptr(X, C.c_float), int(max_steps), _ptr(dump, C.c_uint8),
+                                                 dump.nbytes, _ptr(p1, C.c_float)), "dm_debug_tc_windows")
+        return dump, p1

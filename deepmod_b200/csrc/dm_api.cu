@@ -1,0 +1,511 @@
+// C ABI of deepmod_b200 (include/deepmod_b200.h): context lifetime, weight packing, batch
+// staging, the detect call and the per-position accumulator read-out / BED writer.
+// Everything that computes runs in the CUDA kernels of this library; there is no CPU path.
+#include "dm_common.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+thread_local std::string g_error;
+
+template <typename T>
+int grow(dm_ctx* ctx, T*& p, int64_t n) {
+  if (p) cudaFree(p);
+  p = nullptr;
+  if (n <= 0) n = 1;
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * (size_t)n));
+  return DM_OK;
+}
+
+#define DM_TRY(expr)            \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != DM_OK) return rc__; \
+  } while (0)
+
+int fail(dm_ctx* ctx, int code, const std::string& msg) {
+  dm_set_error(ctx, msg);
+  return code;
+}
+
+uint16_t bf16_bits(float f) {   // round-to-nearest-even, what __float2bfloat16 does
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+float bf16_val(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// ---- weight images ------------------------------------------------------------------
+// fp32 image: see dm_common.cuh (column permutation n' = j*100 + ug*4 + gate).
+void pack_fp32(const float* kernel, const float* bias, int layer, std::vector<float>& W,
+               std::vector<float>& B) {
+  const int K = layer == 0 ? DM_K0_F32 : DM_K12_F32;
+  W.assign((size_t)K * DM_GATES, 0.f);
+  B.assign(DM_GATES, 0.f);
+  for (int u = 0; u < DM_HIDDEN; ++u) {
+    const int j = u / 25, ug = u % 25;
+    for (int g = 0; g < 4; ++g) {
+      const int n_ref = g * DM_HIDDEN + u, n_img = j * 100 + ug * 4 + g;
+      B[n_img] = bias[n_ref];
+      if (layer == 0) {
+        for (int k = 0; k < DM_FNUM; ++k) W[(size_t)k * DM_GATES + n_img] = kernel[(size_t)k * DM_GATES + n_ref];
+        for (int k = 0; k < DM_HIDDEN; ++k)
+          W[(size_t)(8 + k) * DM_GATES + n_img] = kernel[(size_t)(DM_FNUM + k) * DM_GATES + n_ref];
+      } else {
+        for (int k = 0; k < 2 * DM_HIDDEN; ++k) W[(size_t)k * DM_GATES + n_img] = kernel[(size_t)k * DM_GATES + n_ref];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, std::vector<uint16_t>& img);  // dm_lstm_tc.cu
+
+void dm_set_error(dm_ctx* ctx, const std::string& msg) {
+  g_error = msg;
+  if (ctx) ctx->err = msg;
+}
+
+extern "C" {
+
+int dm_version(void) { return 100; }
+
+const char* dm_last_error(const dm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_error.c_str(); }
+
+int dm_create(dm_ctx** out, int device, const dm_weights* w, int precision) {
+  if (!out || !w) return fail(nullptr, DM_ERR_ARG, "dm_create: null argument");
+  *out = nullptr;
+  if (precision != DM_FP32 && precision != DM_BF16) return fail(nullptr, DM_ERR_ARG, "dm_create: bad precision");
+  for (int d = 0; d < 2; ++d)
+    for (int l = 0; l < 3; ++l)
+      if (!w->kernel[d][l] || !w->bias[d][l]) return fail(nullptr, DM_ERR_ARG, "dm_create: missing weight tensor");
+  if (!w->cls_w || !w->cls_b) return fail(nullptr, DM_ERR_ARG, "dm_create: missing classifier tensor");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, DM_ERR_CUDA, std::string("dm_create: no CUDA device (") + cudaGetErrorString(e) +
+                                          "); deepmod_b200 has no CPU path");
+  if (device < 0 || device >= n_dev) return fail(nullptr, DM_ERR_ARG, "dm_create: device out of range");
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, DM_ERR_CUDA, cudaGetErrorString(e));
+  if (prop.major != 10)
+    return fail(nullptr, DM_ERR_CUDA, "dm_create: this library is built for sm_100a (B200) only, found sm_" +
+                                          std::to_string(prop.major) + std::to_string(prop.minor));
+  dm_ctx* ctx = new dm_ctx();
+  ctx->device = device;
+  ctx->precision = precision;
+  ctx->sm_count = prop.multiProcessorCount;
+  auto bail = [&](int rc) { std::string m = ctx->err; dm_destroy(ctx); g_error = m; return rc; };
+#define DM_CK(call)                                                                         \
+  do {                                                                                      \
+    cudaError_t e2 = (call);                                                                \
+    if (e2 != cudaSuccess) { dm_set_error(ctx, std::string(#call) + ": " + cudaGetErrorString(e2)); return bail(DM_ERR_CUDA); } \
+  } while (0)
+  DM_CK(cudaSetDevice(device));
+  DM_CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  DM_CK(cudaEventCreate(&ctx->ev0));
+  DM_CK(cudaEventCreate(&ctx->ev1));
+  DM_CK(cudaEventCreate(&ctx->ev2));
+  DM_CK(cudaEventCreate(&ctx->ev3));
+  std::vector<float> W, B;
+  std::vector<uint16_t> T;
+  for (int d = 0; d < 2; ++d)
+    for (int l = 0; l < 3; ++l) {
+      pack_fp32(w->kernel[d][l], w->bias[d][l], l, W, B);
+      DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.w32[d][l]), W.size() * sizeof(float)));
+      DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.b32[d][l]), B.size() * sizeof(float)));
+      DM_CK(cudaMemcpy(ctx->w.w32[d][l], W.data(), W.size() * sizeof(float), cudaMemcpyHostToDevice));
+      DM_CK(cudaMemcpy(ctx->w.b32[d][l], B.data(), B.size() * sizeof(float), cudaMemcpyHostToDevice));
+      dm_tc_pack_weights(w->kernel[d][l], w->bias[d][l], l, T);
+      DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.wtc[d][l]), T.size() * sizeof(uint16_t)));
+      DM_CK(cudaMemcpy(ctx->w.wtc[d][l], T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+  DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.cls_w), 2 * DM_HIDDEN * 2 * sizeof(float)));
+  DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.cls_b), 2 * sizeof(float)));
+  DM_CK(cudaMemcpy(ctx->w.cls_w, w->cls_w, 2 * DM_HIDDEN * 2 * sizeof(float), cudaMemcpyHostToDevice));
+  DM_CK(cudaMemcpy(ctx->w.cls_b, w->cls_b, 2 * sizeof(float), cudaMemcpyHostToDevice));
+  float cd[2 * DM_HIDDEN];
+  for (int i = 0; i < 2 * DM_HIDDEN; ++i) cd[i] = w->cls_w[i * 2 + 1] - w->cls_w[i * 2 + 0];
+  DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.cls_d), sizeof(cd)));
+  DM_CK(cudaMemcpy(ctx->w.cls_d, cd, sizeof(cd), cudaMemcpyHostToDevice));
+  ctx->w.cls_db = w->cls_b[1] - w->cls_b[0];
+#undef DM_CK
+  *out = ctx;
+  return DM_OK;
+}
+
+void dm_destroy(dm_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int d = 0; d < 2; ++d)
+    for (int l = 0; l < 3; ++l) {
+      cudaFree(ctx->w.w32[d][l]);
+      cudaFree(ctx->w.b32[d][l]);
+      cudaFree(ctx->w.wtc[d][l]);
+    }
+  cudaFree(ctx->w.cls_w); cudaFree(ctx->w.cls_b); cudaFree(ctx->w.cls_d);
+  dm_dev_batch* bs[2] = {&ctx->b, &ctx->fw};
+  for (dm_dev_batch* b : bs) {
+    cudaFree(b->ev_off); cudaFree(b->col_off); cudaFree(b->col_refpos);
+    cudaFree(b->ev_mean); cudaFree(b->ev_stdv); cudaFree(b->ev_len);
+    cudaFree(b->ev_base); cudaFree(b->col_refbase); cudaFree(b->col_readbase);
+    cudaFree(b->start_clip); cudaFree(b->end_clip); cudaFree(b->contig); cudaFree(b->strand);
+    cudaFree(b->win_off); cudaFree(b->col_rank); cudaFree(b->win_col); cudaFree(b->win_frow);
+    cudaFree(b->status); cudaFree(b->feat); cudaFree(b->feat_tc); cudaFree(b->p1); cudaFree(b->pred);
+  }
+  cudaFree(ctx->fw_x);
+  cudaFree(ctx->contig_off_d); cudaFree(ctx->cells);
+  cudaFree(ctx->scratch); cudaFree(ctx->hbuf); cudaFree(ctx->dpart);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int dm_set_precision(dm_ctx* ctx, int precision) {
+  if (!ctx) return DM_ERR_ARG;
+  if (precision != DM_FP32 && precision != DM_BF16) return fail(ctx, DM_ERR_ARG, "dm_set_precision: bad precision");
+  ctx->precision = precision;
+  return DM_OK;
+}
+
+int64_t dm_launch_count(const dm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int dm_last_timing(const dm_ctx* ctx, float* lstm_ms, float* total_ms) {
+  if (!ctx) return DM_ERR_ARG;
+  if (lstm_ms) *lstm_ms = ctx->lstm_ms;
+  if (total_ms) *total_ms = ctx->total_ms;
+  return DM_OK;
+}
+
+}  // extern "C"
+
+// ---- internals shared by the entry points -------------------------------------------
+namespace {
+
+int run_lstm(dm_ctx* ctx, dm_dev_batch& b) {
+  if (b.n_windows == 0) return DM_OK;
+  if (ctx->precision == DM_FP32) return dm_launch_lstm_fp32(ctx, b.feat, b.win_frow, b.n_windows, b.p1, b.pred);
+  return dm_launch_lstm_tc(ctx, b.feat_tc, b.win_frow, b.n_windows, b.p1, b.pred);
+}
+
+// result buffers + feature table for `n_windows` windows over `n_frows` feature rows
+int reserve_windows(dm_ctx* ctx, dm_dev_batch& b, int64_t n_windows, int64_t n_frows) {
+  const int64_t n_pad = dm_pad_windows(n_windows);
+  if (n_pad > b.cap_windows) {
+    const int64_t cap = n_pad + n_pad / 8;
+    DM_TRY(grow(ctx, b.win_col, cap));
+    DM_TRY(grow(ctx, b.win_frow, cap));
+    DM_TRY(grow(ctx, b.p1, cap));
+    DM_TRY(grow(ctx, b.pred, cap));
+    b.cap_windows = cap;
+  }
+  if (n_frows + DM_WINDOW > b.cap_frows) {
+    const int64_t cap = n_frows + n_frows / 8 + DM_WINDOW;
+    DM_TRY(grow(ctx, b.feat, cap * DM_FEAT_STRIDE));
+    DM_TRY(grow(ctx, b.feat_tc, cap * 16));
+    b.cap_frows = cap;
+  }
+  return DM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dm_batch_upload(dm_ctx* ctx, const dm_batch* hb, int64_t* n_windows_out) {
+  if (!ctx || !hb) return DM_ERR_ARG;
+  if (hb->n_reads < 0) return fail(ctx, DM_ERR_ARG, "dm_batch_upload: negative n_reads");
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_dev_batch& b = ctx->b;
+  const int n = hb->n_reads;
+  b.n_reads = n;
+  b.n_events = b.n_cols = b.n_windows = b.n_frows = 0;
+  if (n_windows_out) *n_windows_out = 0;
+  if (n == 0) return DM_OK;
+  if (!hb->ev_off || !hb->col_off || !hb->start_clip || !hb->end_clip || !hb->contig || !hb->strand)
+    return fail(ctx, DM_ERR_ARG, "dm_batch_upload: null per-read array");
+  if (hb->ev_off[0] != 0 || hb->col_off[0] != 0) return fail(ctx, DM_ERR_ARG, "dm_batch_upload: offsets must start at 0");
+  // window offsets: a read contributes L - start_clip - end_clip windows, none if that is
+  // below 50 ('Less Event', myDetect.py:702-705)
+  std::vector<int64_t> win_off((size_t)n + 1, 0);
+  for (int r = 0; r < n; ++r) {
+    const int64_t L = hb->ev_off[r + 1] - hb->ev_off[r], C = hb->col_off[r + 1] - hb->col_off[r];
+    if (L < 0 || C < 0 || hb->start_clip[r] < 0 || hb->end_clip[r] < 0)
+      return fail(ctx, DM_ERR_ARG, "dm_batch_upload: negative length or clip in read " + std::to_string(r));
+    const int64_t lmap = L - hb->start_clip[r] - hb->end_clip[r];
+    win_off[r + 1] = win_off[r] + (lmap >= 50 ? lmap : 0);
+  }
+  const int64_t n_events = hb->ev_off[n], n_cols = hb->col_off[n], n_windows = win_off[n];
+  const int64_t n_frows = n_windows + (int64_t)(2 * DM_FLANK) * n;
+  if (n_frows + DM_WINDOW >= (int64_t)INT32_MAX) return fail(ctx, DM_ERR_ARG, "dm_batch_upload: batch too large (>2^31 rows)");
+  if (n_events > 0 && (!hb->ev_mean || !hb->ev_stdv || !hb->ev_len)) return fail(ctx, DM_ERR_ARG, "dm_batch_upload: null event array");
+  if (n_cols > 0 && (!hb->col_refbase || !hb->col_readbase || !hb->col_refpos)) return fail(ctx, DM_ERR_ARG, "dm_batch_upload: null column array");
+  if (n > b.cap_reads) {
+    const int64_t cap = n + n / 8 + 16;
+    DM_TRY(grow(ctx, b.ev_off, cap + 1)); DM_TRY(grow(ctx, b.col_off, cap + 1)); DM_TRY(grow(ctx, b.win_off, cap + 1));
+    DM_TRY(grow(ctx, b.start_clip, cap)); DM_TRY(grow(ctx, b.end_clip, cap)); DM_TRY(grow(ctx, b.contig, cap));
+    DM_TRY(grow(ctx, b.strand, cap)); DM_TRY(grow(ctx, b.status, cap));
+    b.cap_reads = cap;
+  }
+  if (n_events > b.cap_events) {
+    const int64_t cap = n_events + n_events / 8;
+    DM_TRY(grow(ctx, b.ev_mean, cap)); DM_TRY(grow(ctx, b.ev_stdv, cap)); DM_TRY(grow(ctx, b.ev_len, cap));
+    DM_TRY(grow(ctx, b.ev_base, cap));
+    b.cap_events = cap;
+  }
+  if (n_cols > b.cap_cols) {
+    const int64_t cap = n_cols + n_cols / 8;
+    DM_TRY(grow(ctx, b.col_refbase, cap)); DM_TRY(grow(ctx, b.col_readbase, cap)); DM_TRY(grow(ctx, b.col_refpos, cap));
+    DM_TRY(grow(ctx, b.col_rank, cap));
+    b.cap_cols = cap;
+  }
+  DM_TRY(reserve_windows(ctx, b, n_windows, n_frows));
+  cudaStream_t s = ctx->stream;
+  const auto H2D = cudaMemcpyHostToDevice;
+  DM_CUDA(ctx, cudaMemcpyAsync(b.ev_off, hb->ev_off, sizeof(int64_t) * (n + 1), H2D, s));
+  DM_CUDA(ctx, cudaMemcpyAsync(b.col_off, hb->col_off, sizeof(int64_t) * (n + 1), H2D, s));
+  DM_CUDA(ctx, cudaMemcpyAsync(b.win_off, win_off.data(), sizeof(int64_t) * (n + 1), H2D, s));
+  DM_CUDA(ctx, cudaMemcpyAsync(b.start_clip, hb->start_clip, sizeof(int32_t) * n, H2D, s));
+  DM_CUDA(ctx, cudaMemcpyAsync(b.end_clip, hb->end_clip, sizeof(int32_t) * n, H2D, s));
+  DM_CUDA(ctx, cudaMemcpyAsync(b.contig, hb->contig, sizeof(int32_t) * n, H2D, s));
+  DM_CUDA(ctx, cudaMemcpyAsync(b.strand, hb->strand, sizeof(int8_t) * n, H2D, s));
+  if (n_events > 0) {
+    DM_CUDA(ctx, cudaMemcpyAsync(b.ev_mean, hb->ev_mean, sizeof(float) * n_events, H2D, s));
+    DM_CUDA(ctx, cudaMemcpyAsync(b.ev_stdv, hb->ev_stdv, sizeof(float) * n_events, H2D, s));
+    DM_CUDA(ctx, cudaMemcpyAsync(b.ev_len, hb->ev_len, sizeof(float) * n_events, H2D, s));
+    if (hb->ev_base) DM_CUDA(ctx, cudaMemcpyAsync(b.ev_base, hb->ev_base, n_events, H2D, s));
+  }
+  b.has_ev_base = hb->ev_base != nullptr;
+  if (n_cols > 0) {
+    DM_CUDA(ctx, cudaMemcpyAsync(b.col_refbase, hb->col_refbase, n_cols, H2D, s));
+    DM_CUDA(ctx, cudaMemcpyAsync(b.col_readbase, hb->col_readbase, n_cols, H2D, s));
+    DM_CUDA(ctx, cudaMemcpyAsync(b.col_refpos, hb->col_refpos, sizeof(int64_t) * n_cols, H2D, s));
+  }
+  // win_off.data() is pageable stack/heap memory: the copies above are complete (staged)
+  // only after this synchronize
+  DM_CUDA(ctx, cudaStreamSynchronize(s));
+  b.n_events = n_events; b.n_cols = n_cols; b.n_windows = n_windows; b.n_frows = n_frows;
+  b.prepared = false;
+  ctx->h2d_bytes = sizeof(int64_t) * 3 * (size_t)(n + 1) + (size_t)n * 13 + (size_t)n_events * (hb->ev_base ? 13 : 12) +
+                   (size_t)n_cols * 10;
+  if (n_windows_out) *n_windows_out = n_windows;
+  return DM_OK;
+}
+
+int dm_detect_resident(dm_ctx* ctx, int accumulate) {
+  if (!ctx) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_dev_batch& b = ctx->b;
+  if (b.n_reads == 0) return DM_OK;
+  if (accumulate && ctx->cells == nullptr) return fail(ctx, DM_ERR_STATE, "dm_detect_resident: dm_set_genome not called");
+  cudaStream_t s = ctx->stream;
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+  DM_TRY(dm_launch_prepare(ctx));
+  b.prepared = true;
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+  DM_TRY(run_lstm(ctx, b));
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev2, s));
+  DM_TRY(dm_launch_mask_rejected(ctx));
+  if (accumulate) DM_TRY(dm_launch_accumulate(ctx));
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev3, s));
+  DM_CUDA(ctx, cudaStreamSynchronize(s));
+  DM_CUDA(ctx, cudaEventElapsedTime(&ctx->lstm_ms, ctx->ev1, ctx->ev2));
+  DM_CUDA(ctx, cudaEventElapsedTime(&ctx->total_ms, ctx->ev0, ctx->ev3));
+  return DM_OK;
+}
+
+int dm_fetch_results(dm_ctx* ctx, float* p1_out, uint8_t* pred_out, int32_t* status_out) {
+  if (!ctx) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_dev_batch& b = ctx->b;
+  cudaStream_t s = ctx->stream;
+  const auto D2H = cudaMemcpyDeviceToHost;
+  if (p1_out && b.n_windows > 0) DM_CUDA(ctx, cudaMemcpyAsync(p1_out, b.p1, sizeof(float) * b.n_windows, D2H, s));
+  if (pred_out && b.n_windows > 0) DM_CUDA(ctx, cudaMemcpyAsync(pred_out, b.pred, b.n_windows, D2H, s));
+  if (status_out && b.n_reads > 0) DM_CUDA(ctx, cudaMemcpyAsync(status_out, b.status, sizeof(int32_t) * b.n_reads, D2H, s));
+  DM_CUDA(ctx, cudaStreamSynchronize(s));
+  return DM_OK;
+}
+
+int dm_detect_batch(dm_ctx* ctx, const dm_batch* hb, float* p1_out, uint8_t* pred_out, int32_t* status_out) {
+  if (!ctx || !hb) return DM_ERR_ARG;
+  int64_t nw = 0;
+  DM_TRY(dm_batch_upload(ctx, hb, &nw));
+  DM_TRY(dm_detect_resident(ctx, ctx->cells != nullptr));
+  return dm_fetch_results(ctx, p1_out, pred_out, status_out);
+}
+
+int dm_build_windows(dm_ctx* ctx, float* windows_out) {
+  if (!ctx || !windows_out) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_dev_batch& b = ctx->b;
+  if (b.n_reads == 0 || b.n_windows == 0) return DM_OK;
+  if (!b.prepared) { DM_TRY(dm_launch_prepare(ctx)); b.prepared = true; }
+  const size_t bytes = sizeof(float) * (size_t)b.n_windows * DM_WINDOW * DM_FNUM;
+  float* tmp = nullptr;
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&tmp), bytes));
+  int rc = dm_launch_build_windows(ctx, tmp);
+  cudaError_t e = cudaSuccess;
+  if (rc == DM_OK) {
+    e = cudaMemcpyAsync(windows_out, tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(tmp);
+  if (e != cudaSuccess) return fail(ctx, DM_ERR_CUDA, std::string("dm_build_windows: ") + cudaGetErrorString(e));
+  return rc;
+}
+
+int dm_forward_windows(dm_ctx* ctx, int64_t n, const float* X, float* p1_out, uint8_t* pred_out) {
+  if (!ctx || (n > 0 && !X)) return DM_ERR_ARG;
+  if (n < 0) return fail(ctx, DM_ERR_ARG, "dm_forward_windows: negative n");
+  if (n == 0) return DM_OK;
+  if ((n + 1) * DM_WINDOW >= (int64_t)INT32_MAX) return fail(ctx, DM_ERR_ARG, "dm_forward_windows: too many windows");
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_dev_batch& f = ctx->fw;
+  DM_TRY(reserve_windows(ctx, f, n, n * DM_WINDOW));
+  if (n > ctx->fw_x_cap) {
+    DM_TRY(grow(ctx, ctx->fw_x, (n + n / 8) * DM_WINDOW * DM_FNUM));
+    ctx->fw_x_cap = n + n / 8;
+  }
+  cudaStream_t s = ctx->stream;
+  DM_CUDA(ctx, cudaMemcpyAsync(ctx->fw_x, X, sizeof(float) * (size_t)n * DM_WINDOW * DM_FNUM, cudaMemcpyHostToDevice, s));
+  f.n_windows = n;
+  f.n_frows = n * DM_WINDOW;
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
+  DM_TRY(dm_launch_windows_to_rows(ctx, ctx->fw_x, n, f.feat, f.feat_tc, f.win_frow));
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev1, s));
+  DM_TRY(run_lstm(ctx, f));
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev2, s));
+  if (p1_out) DM_CUDA(ctx, cudaMemcpyAsync(p1_out, f.p1, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+  if (pred_out) DM_CUDA(ctx, cudaMemcpyAsync(pred_out, f.pred, n, cudaMemcpyDeviceToHost, s));
+  DM_CUDA(ctx, cudaStreamSynchronize(s));
+  DM_CUDA(ctx, cudaEventElapsedTime(&ctx->lstm_ms, ctx->ev1, ctx->ev2));
+  DM_CUDA(ctx, cudaEventElapsedTime(&ctx->total_ms, ctx->ev0, ctx->ev2));
+  return DM_OK;
+}
+
+// ---- accumulator -----------------------------------------------------------------------
+int dm_set_genome(dm_ctx* ctx, int32_t n_contigs, const int64_t* contig_len, char base) {
+  if (!ctx || n_contigs <= 0 || !contig_len) return DM_ERR_ARG;
+  if (base != 'A' && base != 'C' && base != 'G' && base != 'T') return fail(ctx, DM_ERR_ARG, "dm_set_genome: base must be one of ACGT");
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> off((size_t)n_contigs + 1, 0);
+  for (int i = 0; i < n_contigs; ++i) {
+    if (contig_len[i] < 0) return fail(ctx, DM_ERR_ARG, "dm_set_genome: negative contig length");
+    off[i + 1] = off[i] + contig_len[i];
+  }
+  cudaFree(ctx->cells); ctx->cells = nullptr;
+  cudaFree(ctx->contig_off_d); ctx->contig_off_d = nullptr;
+  ctx->n_cells = 2 * off[n_contigs];
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->cells), sizeof(unsigned long long) * (size_t)std::max<int64_t>(ctx->n_cells, 1)));
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->contig_off_d), sizeof(int64_t) * off.size()));
+  DM_CUDA(ctx, cudaMemcpy(ctx->contig_off_d, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice));
+  ctx->n_contigs = n_contigs;
+  ctx->contig_len.assign(contig_len, contig_len + n_contigs);
+  ctx->contig_off = off;
+  ctx->base = base;
+  return dm_hist_clear(ctx);
+}
+
+int dm_hist_clear(dm_ctx* ctx) {
+  if (!ctx) return DM_ERR_ARG;
+  if (!ctx->cells) return fail(ctx, DM_ERR_STATE, "dm_hist_clear: dm_set_genome not called");
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  DM_CUDA(ctx, cudaMemsetAsync(ctx->cells, 0, sizeof(unsigned long long) * (size_t)ctx->n_cells, ctx->stream));
+  DM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return DM_OK;
+}
+
+int dm_hist_device_ptr(dm_ctx* ctx, void** cells_d, int64_t* n_cells) {
+  if (!ctx || !cells_d || !n_cells) return DM_ERR_ARG;
+  if (!ctx->cells) return fail(ctx, DM_ERR_STATE, "dm_hist_device_ptr: dm_set_genome not called");
+  *cells_d = ctx->cells;
+  *n_cells = ctx->n_cells;
+  return DM_OK;
+}
+
+int dm_hist_nonzero(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t cap, int64_t* pos, int32_t* cov,
+                    int32_t* mod, int64_t* n_rows) {
+  if (!ctx || !n_rows) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> p; std::vector<int32_t> c, m;
+  DM_TRY(dm_hist_compact(ctx, contig, strand, p, c, m));
+  *n_rows = (int64_t)p.size();
+  if (pos && cov && mod) {
+    const int64_t k = std::min<int64_t>(cap, (int64_t)p.size());
+    if (k > 0) {
+      memcpy(pos, p.data(), sizeof(int64_t) * k);
+      memcpy(cov, c.data(), sizeof(int32_t) * k);
+      memcpy(mod, m.data(), sizeof(int32_t) * k);
+    }
+  }
+  return DM_OK;
+}
+
+int dm_write_bed(dm_ctx* ctx, int32_t contig, int8_t strand, const char* chrom, const char* path, int64_t* n_rows) {
+  if (!ctx || !chrom || !path) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> p; std::vector<int32_t> c, m;
+  DM_TRY(dm_hist_compact(ctx, contig, strand, p, c, m));
+  if (n_rows) *n_rows = (int64_t)p.size();
+  if (p.empty()) return DM_OK;                    // myDetect.py:1109: no keys, no file
+  FILE* fh = fopen(path, "w");
+  if (!fh) return fail(ctx, DM_ERR_IO, std::string("dm_write_bed: cannot open ") + path);
+  const char sc = strand >= 0 ? '+' : '-';
+  for (size_t i = 0; i < p.size(); ++i) {
+    // myDetect.py:1116-1120: ' '.join([chr, pos, pos+1, base, min(cov,1000), strand, pos, pos+1,
+    //                                 '0,0,0', cov, '%d' % (100*mod/(cov or 1)), mod, '\n'])
+    const long long pos = p[i], cov = c[i], mod = m[i];
+    fprintf(fh, "%s %lld %lld %c %lld %c %lld %lld 0,0,0 %lld %lld %lld \n", chrom, pos, pos + 1, ctx->base,
+            cov > 1000 ? 1000LL : cov, sc, pos, pos + 1, cov, (100 * mod) / (cov > 0 ? cov : 1), mod);
+  }
+  if (fclose(fh) != 0) return fail(ctx, DM_ERR_IO, std::string("dm_write_bed: write failed for ") + path);
+  return DM_OK;
+}
+
+int dm_debug_tc_windows(dm_ctx* ctx, int64_t n, const float* X, int max_steps, uint8_t* dump, int64_t dump_cap,
+                        float* p1_out) {
+  if (!ctx || n <= 0 || !X) return DM_ERR_ARG;
+  if ((n + 1) * DM_WINDOW >= (int64_t)INT32_MAX) return fail(ctx, DM_ERR_ARG, "dm_debug_tc_windows: too many windows");
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_dev_batch& f = ctx->fw;
+  DM_TRY(reserve_windows(ctx, f, n, n * DM_WINDOW));
+  if (n > ctx->fw_x_cap) {
+    DM_TRY(grow(ctx, ctx->fw_x, (n + n / 8) * DM_WINDOW * DM_FNUM));
+    ctx->fw_x_cap = n + n / 8;
+  }
+  cudaStream_t s = ctx->stream;
+  DM_CUDA(ctx, cudaMemcpyAsync(ctx->fw_x, X, sizeof(float) * (size_t)n * DM_WINDOW * DM_FNUM, cudaMemcpyHostToDevice, s));
+  f.n_windows = n;
+  f.n_frows = n * DM_WINDOW;
+  DM_TRY(dm_launch_windows_to_rows(ctx, ctx->fw_x, n, f.feat, f.feat_tc, f.win_frow));
+  DM_TRY(dm_tc_debug(ctx, f.feat_tc, f.win_frow, n, f.p1, f.pred, max_steps, dump, dump_cap));
+  if (p1_out) DM_CUDA(ctx, cudaMemcpy(p1_out, f.p1, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return DM_OK;
+}
+
+int dm_selftest_umma(dm_ctx* ctx, int n, int k, float* max_err) {
+  if (!ctx || !max_err) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  return dm_tc_selftest(ctx, n, k, max_err);
+}
+
+}  // extern "C"

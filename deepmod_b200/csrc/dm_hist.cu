@@ -1,0 +1,208 @@
+// Label write-back + per-position accumulation, fused.
+//
+// Reference behaviour (bin/DeepMod_scripts/myDetect.py):
+//   mPredict1 :822-833  prediction m of a read belongs to its m-th non-gap alignment column;
+//   sum_handler :1089-1100  for every column whose refbase == --Base: create the key
+//       (chr, strand, refpos); if readbase != '-': cov += 1, and mod += 1 when mod_pred == 1.
+// A key exists as soon as a column touches it, even a deletion, so the cell keeps a third
+// counter (deletion touches) next to cov and mod: row exists <=> cell != 0.
+#include "dm_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int find_segment(const int64_t* __restrict__ off, int n, int64_t x) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (off[mid] <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void k_accumulate(int n_reads, int64_t n_cols, const int64_t* __restrict__ col_off,
+                             const int64_t* __restrict__ col_rank, const uint8_t* __restrict__ refbase,
+                             const uint8_t* __restrict__ readbase, const int64_t* __restrict__ refpos,
+                             const int32_t* __restrict__ contig, const int8_t* __restrict__ strand,
+                             const int32_t* __restrict__ status, const int64_t* __restrict__ win_off,
+                             const uint8_t* __restrict__ pred, const int64_t* __restrict__ contig_off,
+                             const int64_t* __restrict__ contig_len_cum, int n_contigs,
+                             unsigned long long* __restrict__ cells, uint8_t base) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  if (refbase[c] != base) return;                          // :1091 (base is one of A,C,G,T)
+  int r = find_segment(col_off, n_reads, c);
+  if (status[r] != DM_READ_OK) return;                     // read skipped at :712 / :702
+  int ct = contig[r];
+  if (ct < 0 || ct >= n_contigs) return;
+  int64_t p = refpos[c];
+  int64_t len = contig_off[ct + 1] - contig_off[ct];
+  if (p < 0 || p >= len) return;
+  unsigned long long add;
+  if (readbase[c] == '-') {
+    add = 1ull << DM_CELL_DEL_SHIFT;                       // key created, nothing counted
+  } else {
+    int64_t k = col_rank[c] - col_rank[col_off[r]];
+    add = 1ull << DM_CELL_COV_SHIFT;
+    if (pred[win_off[r] + k] == 1) add |= 1ull << DM_CELL_MOD_SHIFT;
+  }
+  // cells: per contig, [+ strand | - strand] blocks of contig length
+  int64_t cell = 2 * contig_off[ct] + (strand[r] >= 0 ? 0 : len) + p;
+  atomicAdd(&cells[cell], add);
+}
+
+// Windows of reads rejected on the device (mismatch / bad alignment) report p1 = 0, pred = 0:
+// the reference never predicts them (myDetect.py:712).  One CTA per read.
+__global__ void k_mask_rejected(const int32_t* __restrict__ status, const int64_t* __restrict__ win_off,
+                                float* __restrict__ p1, uint8_t* __restrict__ pred) {
+  const int r = blockIdx.x;
+  if (status[r] == DM_READ_OK) return;
+  for (int64_t w = win_off[r] + threadIdx.x; w < win_off[r + 1]; w += blockDim.x) {
+    p1[w] = 0.f;
+    pred[w] = 0;
+  }
+}
+
+// two-pass compaction of the non-zero cells of one (contig, strand) block
+__global__ void k_count_nonzero(const unsigned long long* __restrict__ cells, int64_t n,
+                                int* __restrict__ block_cnt) {
+  __shared__ int wsum[8];
+  int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) cnt += (i + j < n) && (cells[i + j] != 0ull);
+  for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int w = 0; w < 8; ++w) s += wsum[w];
+    block_cnt[blockIdx.x] = s;
+  }
+}
+
+__global__ void k_scan_blocks(int* __restrict__ block_cnt, int n_blocks, int64_t* __restrict__ block_off,
+                              int64_t* __restrict__ total) {
+  // single thread block, sequential chunks of 1024
+  __shared__ int64_t buf[1024];
+  __shared__ int64_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_blocks; base += 1024) {
+    int i = base + threadIdx.x;
+    int64_t v = i < n_blocks ? block_cnt[i] : 0;
+    buf[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int64_t t = threadIdx.x >= o ? buf[threadIdx.x - o] : 0;
+      __syncthreads();
+      buf[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < n_blocks) block_off[i] = carry + buf[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += buf[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void k_emit_nonzero(const unsigned long long* __restrict__ cells, int64_t n,
+                               const int64_t* __restrict__ block_off, int64_t cap,
+                               int64_t* __restrict__ pos, int32_t* __restrict__ cov, int32_t* __restrict__ mod) {
+  __shared__ int wtot[8];
+  int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x * 4;
+  unsigned long long v[4];
+  int cnt = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[j] = (i + j < n) ? cells[i + j] : 0ull;
+    cnt += v[j] != 0ull;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = cnt;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wtot[warp] = incl;
+  __syncthreads();
+  int wbase = 0;
+  for (int w = 0; w < warp; ++w) wbase += wtot[w];
+  int64_t o = block_off[blockIdx.x] + wbase + incl - cnt;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (v[j] != 0ull) {
+      if (o < cap) {
+        pos[o] = i + j;
+        cov[o] = (int32_t)((v[j] >> DM_CELL_COV_SHIFT) & DM_CELL_MASK);
+        mod[o] = (int32_t)((v[j] >> DM_CELL_MOD_SHIFT) & DM_CELL_MASK);
+      }
+      ++o;
+    }
+  }
+}
+
+}  // namespace
+
+int dm_launch_accumulate(dm_ctx* ctx) {
+  dm_dev_batch& b = ctx->b;
+  if (b.n_cols == 0 || ctx->cells == nullptr) return DM_OK;
+  unsigned blocks = (unsigned)((b.n_cols + 255) / 256);
+  k_accumulate<<<blocks, 256, 0, ctx->stream>>>(
+      b.n_reads, b.n_cols, b.col_off, b.col_rank, b.col_refbase, b.col_readbase, b.col_refpos,
+      b.contig, b.strand, b.status, b.win_off, b.pred, ctx->contig_off_d, nullptr, ctx->n_contigs,
+      ctx->cells, (uint8_t)ctx->base);
+  ctx->launches += 1;
+  DM_CUDA(ctx, cudaGetLastError());
+  return DM_OK;
+}
+
+int dm_launch_mask_rejected(dm_ctx* ctx) {
+  dm_dev_batch& b = ctx->b;
+  if (b.n_reads == 0 || b.n_windows == 0) return DM_OK;
+  k_mask_rejected<<<b.n_reads, 128, 0, ctx->stream>>>(b.status, b.win_off, b.p1, b.pred);
+  ctx->launches += 1;
+  DM_CUDA(ctx, cudaGetLastError());
+  return DM_OK;
+}
+
+int dm_hist_compact(dm_ctx* ctx, int32_t contig, int8_t strand, std::vector<int64_t>& pos,
+                    std::vector<int32_t>& cov, std::vector<int32_t>& mod) {
+  pos.clear(); cov.clear(); mod.clear();
+  if (ctx->cells == nullptr) { dm_set_error(ctx, "dm_set_genome not called"); return DM_ERR_STATE; }
+  if (contig < 0 || contig >= ctx->n_contigs) { dm_set_error(ctx, "contig out of range"); return DM_ERR_ARG; }
+  const int64_t len = ctx->contig_len[contig];
+  if (len == 0) return DM_OK;
+  const unsigned long long* blk = ctx->cells + 2 * ctx->contig_off[contig] + (strand >= 0 ? 0 : len);
+  const int n_blocks = (int)((len + 1023) / 1024);
+  int* block_cnt = nullptr;
+  int64_t* block_off = nullptr;
+  DM_CUDA(ctx, cudaMalloc(&block_cnt, sizeof(int) * (size_t)n_blocks));
+  DM_CUDA(ctx, cudaMalloc(&block_off, sizeof(int64_t) * (size_t)(n_blocks + 1)));
+  int64_t* total_d = block_off + n_blocks;
+  k_count_nonzero<<<n_blocks, 256, 0, ctx->stream>>>(blk, len, block_cnt);
+  k_scan_blocks<<<1, 1024, 0, ctx->stream>>>(block_cnt, n_blocks, block_off, total_d);
+  ctx->launches += 2;
+  int64_t total = 0;
+  cudaError_t e = cudaMemcpyAsync(&total, total_d, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  int rc = DM_OK;
+  int64_t *pos_d = nullptr; int32_t *cov_d = nullptr, *mod_d = nullptr;
+  if (e == cudaSuccess && total > 0) {
+    e = cudaMalloc(&pos_d, sizeof(int64_t) * (size_t)total);
+    if (e == cudaSuccess) e = cudaMalloc(&cov_d, sizeof(int32_t) * (size_t)total);
+    if (e == cudaSuccess) e = cudaMalloc(&mod_d, sizeof(int32_t) * (size_t)total);
+    if (e == cudaSuccess) {
+      k_emit_nonzero<<<n_blocks, 256, 0, ctx->stream>>>(blk, len, block_off, total, pos_d, cov_d, mod_d);
+      ctx->launches += 1;
+      pos.resize(total); cov.resize(total); mod.resize(total);
+      e = cudaMemcpyAsync(pos.data(), pos_d, sizeof(int64_t) * total, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(cov.data(), cov_d, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(mod.data(), mod_d, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+  }
+  if (e != cudaSuccess) { dm_set_error(ctx, std::string("dm_hist_compact: ") + cudaGetErrorString(e)); rc = DM_ERR_CUDA; }
+  cudaFree(pos_d); cudaFree(cov_d); cudaFree(mod_d); cudaFree(block_cnt); cudaFree(block_off);
+  return rc;
+}

@@ -1,0 +1,593 @@
+// bf16 tensor-core path of the BiLSTM (tcgen05 / TMEM / bulk-TMA), sm_100a only.
+//
+// Same graph as dm_lstm_fp32.cu (bin/DeepMod_scripts/myMultiBiRNN.py:30-61, 66 live
+// cell-steps), restructured for the B200:
+//
+//  * one CTA owns 128 windows (= the 128 TMEM lanes / UMMA M) for both directions;
+//  * every cell-step is ONE logical GEMM  gates[128,400] = A[128,K] * W[K,400]  issued as
+//    5 N-chunks of 80 gate columns (20 units x {i,j,f,o}) into a 6-slot TMEM ring, so the
+//    tensor pipe fills slot c+1.. while the epilogue warps drain slot c;
+//  * A is never materialised per step: it is the concatenation of the resident bf16 hidden
+//    tiles (K-major core-matrix columns of 128 rows x 16 B).  Each hidden tile carries 4
+//    extra K slots (1, 1, mean_lo, stdv_lo): the bias rides in the GEMM as a bf16 hi/lo
+//    pair against the constant ones, the signal features as hi/lo pairs;
+//  * the three layers are walked in wavefront order (t+l = const), which makes consecutive
+//    cell-steps independent: MMA of step g+1 overlaps the epilogue of step g.  h0/h1 are
+//    double-buffered on the parity of t for that;
+//  * weights (bf16, 0.5 folded into the sigmoid gates, forget bias folded into the bias)
+//    stream from L2 through a 4-stage shared-memory ring with cp.async.bulk + mbarriers,
+//    pre-arranged on the host in the exact UMMA canonical (no-swizzle, K-major) layout;
+//  * the epilogue (20 warps) reads 16 TMEM columns = 4 units per thread and chunk, applies
+//    sigmoid(x) = 0.5*tanh(x/2)+0.5 and tanh with one MUFU each, keeps the cell state in
+//    packed fp16 registers and writes h back as bf16 straight into the next A operand.
+#include "dm_common.cuh"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace {
+
+constexpr int TC_CTRL_WARPS = 4;        // 0: weight producer, 1: MMA issuer, 2: TMEM alloc, 3: idle
+constexpr int TC_EPI_WARPS = 20;        // 4 lane quarters x 5 column groups
+constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
+constexpr int TC_THREADS = (TC_CTRL_WARPS + TC_EPI_WARPS) * 32;
+constexpr int TC_CHUNK_N = 80;          // gate columns per MMA and TMEM slot
+constexpr int TC_NCHUNK = 5;
+constexpr int TC_TSLOTS = 6;
+constexpr int TC_ACOL = 2048;           // A core column: 128 rows x 16 B
+constexpr int TC_HCOLS = 13;            // 100 units + 4 extra K slots
+constexpr int TC_HTILE = TC_HCOLS * TC_ACOL;
+constexpr int TC_BCOL = TC_CHUNK_N * 16;   // B core column of one chunk: 80 n x 16 B
+constexpr int TC_STAGE_COLS = 14;
+constexpr int TC_STAGE = TC_STAGE_COLS * TC_BCOL;
+constexpr int TC_NSTAGE = 4;
+constexpr int TC_STEPS_PER_DIR = 33;
+
+constexpr int OFF_X = 0;                                   // 2 x-columns
+constexpr int OFF_H0 = OFF_X + 2 * TC_ACOL;                // h0[2]
+constexpr int OFF_H1 = OFF_H0 + 2 * TC_HTILE;              // h1[2]
+constexpr int OFF_H2 = OFF_H1 + 2 * TC_HTILE;              // h2
+constexpr int OFF_W = OFF_H2 + TC_HTILE;                   // weight ring
+constexpr int OFF_BAR = OFF_W + TC_NSTAGE * TC_STAGE;
+constexpr int BAR_FULL = 0, BAR_EMPTY = 4, BAR_TFULL = 8, BAR_TEMPTY = 14, BAR_HDONE = 20, N_BARS = 22;
+constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
+constexpr int OFF_PART = OFF_TMEM + 16;                    // float part[5][128]
+constexpr int OFF_FROW = OFF_PART + 5 * 128 * 4;           // int frow[128]
+constexpr int OFF_CLS = OFF_FROW + 128 * 4;                // float cls_d[2][100]
+constexpr int TC_SMEM = OFF_CLS + 200 * 4;
+static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_alloc(uint32_t smem_dst) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_dst) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc(uint32_t taddr) {    // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, M = 128
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
+
+// UMMA shared-memory descriptor, K-major, no swizzle: 8-row core matrices of 128 contiguous
+// bytes; `lbo` = byte distance between the two K-adjacent core matrices of one K=16 step,
+// `sbo` = byte distance between 8-row groups.  (cute::UMMA::SmemDescriptor, version 1.)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float tanh_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// feature row of time index tau (0..10 in processing order) of a window
+__device__ __forceinline__ int tau_row(int dir, int tau) { return dir == 0 ? tau : DM_WINDOW - 1 - tau; }
+
+// ---- the kernel -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__ win_frow, dm_dev_weights w,
+          float* __restrict__ p1_out, uint8_t* __restrict__ pred_out, int max_steps, unsigned char* __restrict__ dbg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + OFF_BAR;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t win0 = (int64_t)blockIdx.x * DM_TILE_M;
+  int* s_frow = reinterpret_cast<int*>(smem + OFF_FROW);
+  float* s_part = reinterpret_cast<float*>(smem + OFF_PART);
+  float* s_cls = reinterpret_cast<float*>(smem + OFF_CLS);
+  volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
+
+  // ---- one-time setup ----
+  if (tid < DM_TILE_M) s_frow[tid] = win_frow[win0 + tid];
+  if (tid < 200) s_cls[tid] = w.cls_d[tid];
+  if (tid == 0) {
+    for (int i = 0; i < TC_NSTAGE; ++i) { mbar_init(bar0 + 8 * (BAR_FULL + i), 1); mbar_init(bar0 + 8 * (BAR_EMPTY + i), 1); }
+    for (int i = 0; i < TC_TSLOTS; ++i) { mbar_init(bar0 + 8 * (BAR_TFULL + i), 1); mbar_init(bar0 + 8 * (BAR_TEMPTY + i), TC_EPI_WARPS); }
+    mbar_init(bar0 + 8 * (BAR_HDONE + 0), TC_EPI_WARPS);
+    mbar_init(bar0 + 8 * (BAR_HDONE + 1), TC_EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tc_alloc(sbase + OFF_TMEM);
+  __syncthreads();     // frow visible to the epilogue's init below
+
+  // epilogue-side state (only meaningful for warps >= 4)
+  const int e = warp - TC_CTRL_WARPS;
+  const int q = warp & 3;                    // TMEM lane quarter this warp may touch
+  const int sgrp = e >> 2;                   // column group 0..4 (4 units per chunk)
+  const int row = q * 32 + lane;             // window within the tile
+  const uint32_t row_off = (uint32_t)((row >> 3) * 128 + (row & 7) * 16);
+
+  // direction init: zero the hidden tiles, stage x(0), x(1) and the step-0 extras of h0[1]
+  auto dir_init = [&](int dir) {
+    const int et = tid - TC_CTRL_WARPS * 32;
+    uint4 z = make_uint4(0, 0, 0, 0);
+    for (int i = et; i < (5 * TC_HTILE) / 16; i += TC_EPI_THREADS)
+      *reinterpret_cast<uint4*>(smem + OFF_H0 + i * 16) = z;
+    epi_bar();
+    if (et < 256) {
+      const int r = et & 127, tau = et >> 7;
+      const uint4 v = *reinterpret_cast<const uint4*>(feat_tc + ((int64_t)s_frow[r] + tau_row(dir, tau)) * 16);
+      *reinterpret_cast<uint4*>(smem + OFF_X + tau * TC_ACOL + (r >> 3) * 128 + (r & 7) * 16) = v;
+    } else if (et < 384) {
+      const int r = et - 256;
+      const uint2 v = *reinterpret_cast<const uint2*>(feat_tc + ((int64_t)s_frow[r] + tau_row(dir, 0)) * 16 + 8);
+      *reinterpret_cast<uint2*>(smem + OFF_H0 + TC_HTILE + 12 * TC_ACOL + (r >> 3) * 128 + (r & 7) * 16 + 8) = v;
+    }
+    fence_async_smem();
+    epi_bar();
+  };
+  if (warp >= TC_CTRL_WARPS) {
+    for (int i = tid - TC_CTRL_WARPS * 32; i < 5 * 128; i += TC_EPI_THREADS) s_part[i] = 0.f;
+    dir_init(0);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp == 0) {
+    // ================= weight producer =================
+    if (lane == 0) {
+      uint32_t st = 0;
+      int g = 0;
+      for (int dir = 0; dir < 2; ++dir)
+        for (int d = 0; d < 13; ++d)
+          for (int l = 0; l < 3; ++l) {
+            const int t = d - l;
+            if (t < 0 || t > 10) continue;
+            if (g++ >= max_steps) continue;
+            const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(w.wtc[dir][l]);
+            const int ncols = l == 0 ? 14 : 26;
+            for (int j = 0; j < TC_NCHUNK; ++j) {
+              for (int half = 0; half < (l == 0 ? 1 : 2); ++half) {
+                const uint32_t slot = st & (TC_NSTAGE - 1), use = st / TC_NSTAGE;
+                if (use > 0) mbar_wait(bar0 + 8 * (BAR_EMPTY + slot), (use - 1) & 1);
+                const uint32_t bytes = (half == 0 ? 14 : 12) * TC_BCOL;
+                mbar_expect_tx(bar0 + 8 * (BAR_FULL + slot), bytes);
+                bulk_g2s(sbase + OFF_W + slot * TC_STAGE, wsrc + (size_t)(j * ncols + half * 14) * TC_BCOL, bytes,
+                         bar0 + 8 * (BAR_FULL + slot));
+                ++st;
+              }
+            }
+          }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(128, TC_CHUNK_N);
+      uint32_t st = 0, tslot = 0, tuse = 0;
+      int g = 0;
+      for (int dir = 0; dir < 2; ++dir)
+        for (int d = 0; d < 13; ++d)
+          for (int l = 0; l < 3; ++l) {
+            const int t = d - l;
+            if (t < 0 || t > 10) continue;
+            if (g >= max_steps) { ++g; continue; }
+            // inputs of this cell-step were written by the epilogues of steps <= g-2, or g-1 in
+            // the fill/drain corners of the wavefront (and across the direction switch)
+            if (g >= 2) mbar_wait(bar0 + 8 * (BAR_HDONE + (g & 1)), ((g - 2) >> 1) & 1);
+            const bool wait1 = (d == 0 && dir > 0) || (d == 1 && l == 0) || d == 12;
+            if (wait1 && g >= 1) mbar_wait(bar0 + 8 * (BAR_HDONE + ((g - 1) & 1)), ((g - 1) >> 1) & 1);
+            tc_fence_after();
+            uint32_t base0, base1;
+            int n0;
+            if (l == 0)      { base0 = sbase + OFF_X + (t & 1) * TC_ACOL;   n0 = 1;        base1 = sbase + OFF_H0 + ((t + 1) & 1) * TC_HTILE; }
+            else if (l == 1) { base0 = sbase + OFF_H0 + (t & 1) * TC_HTILE; n0 = TC_HCOLS; base1 = sbase + OFF_H1 + ((t + 1) & 1) * TC_HTILE; }
+            else             { base0 = sbase + OFF_H1 + (t & 1) * TC_HTILE; n0 = TC_HCOLS; base1 = sbase + OFF_H2; }
+            for (int j = 0; j < TC_NCHUNK; ++j) {
+              if (tuse > 0) { mbar_wait(bar0 + 8 * (BAR_TEMPTY + tslot), (tuse - 1) & 1); tc_fence_after(); }
+              const uint32_t d_tmem = tmem_base + tslot * TC_CHUNK_N;
+              int k16 = 0;
+              for (int half = 0; half < (l == 0 ? 1 : 2); ++half) {
+                const uint32_t slot = st & (TC_NSTAGE - 1), use = st / TC_NSTAGE;
+                mbar_wait(bar0 + 8 * (BAR_FULL + slot), use & 1);
+                tc_fence_after();
+                const uint32_t wb = sbase + OFF_W + slot * TC_STAGE;
+                const int nk = half == 0 ? 7 : 6;
+                for (int i = 0; i < nk; ++i, ++k16) {
+                  const int v0 = 2 * k16, v1 = v0 + 1;
+                  const uint32_t a0 = v0 < n0 ? base0 + v0 * TC_ACOL : base1 + (v0 - n0) * TC_ACOL;
+                  const uint32_t a1 = v1 < n0 ? base0 + v1 * TC_ACOL : base1 + (v1 - n0) * TC_ACOL;
+                  tc_mma(d_tmem, umma_desc(a0, a1 - a0, 128), umma_desc(wb + i * 2 * TC_BCOL, TC_BCOL, 128), idesc,
+                         k16 > 0 ? 1u : 0u);
+                }
+                tc_commit(bar0 + 8 * (BAR_EMPTY + slot));     // stage free once these MMAs retire
+                ++st;
+              }
+              tc_commit(bar0 + 8 * (BAR_TFULL + tslot));      // accumulator chunk ready
+              if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
+            }
+            ++g;
+          }
+    }
+  } else if (warp >= TC_CTRL_WARPS) {
+    // ================= epilogue: gates -> (c, h) =================
+    __half2 cst[3][TC_NCHUNK][2];
+    uint32_t tslot = 0, tuse = 0;
+    int g = 0;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sgrp * 16;
+    for (int dir = 0; dir < 2; ++dir) {
+#pragma unroll
+      for (int l = 0; l < 3; ++l)
+#pragma unroll
+        for (int j = 0; j < TC_NCHUNK; ++j) cst[l][j][0] = cst[l][j][1] = __floats2half2_rn(0.f, 0.f);
+      float cls_acc = 0.f;
+      for (int d = 0; d < 13; ++d) {
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+          const int t = d - l;
+          if (t < 0 || t > 10) continue;
+          if (g >= max_steps) { ++g; continue; }
+          // prefetch what this step's epilogue must stage for later steps
+          uint4 xnext = make_uint4(0, 0, 0, 0);
+          uint2 lows = make_uint2(0, 0);
+          if (l == 0) {
+            if (sgrp == 0 && t + 2 <= 10)
+              xnext = *reinterpret_cast<const uint4*>(feat_tc + ((int64_t)s_frow[row] + tau_row(dir, t + 2)) * 16);
+            if (sgrp == 4)   // (1, 1, mean_lo, stdv_lo) of the next time index ride in h0's extras
+              lows = *reinterpret_cast<const uint2*>(feat_tc + ((int64_t)s_frow[row] + tau_row(dir, t + 1 <= 10 ? t + 1 : 10)) * 16 + 8);
+          } else if (l == 1) {
+            lows = make_uint2(0x3F803F80u, 0u);     // (1, 1, 0, 0): bias carriers for layer 2
+          }
+          const uint32_t htile = l == 0 ? OFF_H0 + (t & 1) * TC_HTILE : l == 1 ? OFF_H1 + (t & 1) * TC_HTILE : OFF_H2;
+#pragma unroll
+          for (int j = 0; j < TC_NCHUNK; ++j) {
+            mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+            tc_fence_after();
+            uint32_t v[16];
+            tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_TEMPTY + tslot));
+            if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
+            float hn[4];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              const float2 cp = __half22float2(cst[l][j][p]);
+              float cn[2];
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int u = 2 * p + k;
+                const float ti = tanh_mufu(__uint_as_float(v[4 * u + 0]));
+                const float tj = tanh_mufu(__uint_as_float(v[4 * u + 1]));
+                const float tf = tanh_mufu(__uint_as_float(v[4 * u + 2]));
+                const float to = tanh_mufu(__uint_as_float(v[4 * u + 3]));
+                const float si = fmaf(ti, 0.5f, 0.5f), sf = fmaf(tf, 0.5f, 0.5f), so = fmaf(to, 0.5f, 0.5f);
+                cn[k] = fmaf(k == 0 ? cp.x : cp.y, sf, si * tj);
+                hn[u] = tanh_mufu(cn[k]) * so;
+              }
+              cst[l][j][p] = __floats2half2_rn(cn[0], cn[1]);
+            }
+            if (l == 2 && t == 10) {
+              const float* cw = s_cls + dir * DM_HIDDEN + 20 * j + 4 * sgrp;
+              cls_acc += hn[0] * cw[0] + hn[1] * cw[1] + hn[2] * cw[2] + hn[3] * cw[3];
+            }
+            // units u0..u0+3, u0 = 20 j + 4 sgrp: core column u0/8, byte (u0%8)*2 of the row's 16 B
+            const int u0 = 20 * j + 4 * sgrp;
+            unsigned char* dst = smem + htile + (u0 >> 3) * TC_ACOL + row_off + (u0 & 7) * 2;
+            const uint32_t h01 = pack_bf16(hn[0], hn[1]), h23 = pack_bf16(hn[2], hn[3]);
+            if (j == TC_NCHUNK - 1 && sgrp == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(h01, h23, lows.x, lows.y);
+            else *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
+          }
+          if (l == 0 && sgrp == 0 && t + 2 <= 10)
+            *reinterpret_cast<uint4*>(smem + OFF_X + (t & 1) * TC_ACOL + row_off) = xnext;
+          if (l == 2 && t == 10) s_part[sgrp * 128 + row] += cls_acc;
+          if (dir == 0 && d == 12 && max_steps > TC_STEPS_PER_DIR) {
+            epi_bar();          // every warp is done with direction 0
+            dir_init(1);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_HDONE + (g & 1)));
+          ++g;
+        }
+      }
+    }
+    epi_bar();
+    if (sgrp == 0) {
+      float dl = w.cls_db;
+#pragma unroll
+      for (int s = 0; s < 5; ++s) dl += s_part[s * 128 + row];
+      // softmax over two classes: p1 = 1/(1+exp(l0-l1)); argmax picks class 1 iff l1 > l0
+      if (p1_out) p1_out[win0 + row] = 1.0f / (1.0f + __expf(-dl));
+      if (pred_out) pred_out[win0 + row] = dl > 0.f ? 1 : 0;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (dbg != nullptr && blockIdx.x == 0)
+    for (int i = tid; i < OFF_W / 16; i += TC_THREADS)
+      reinterpret_cast<uint4*>(dbg)[i] = *reinterpret_cast<const uint4*>(smem + i * 16);
+  if (warp == 2) { tc_fence_after(); tc_dealloc(tmem_base); }
+}
+
+// ---- descriptor / TMEM / bulk-copy self-test: D[128,n] = A[128,k] * B[n,k]^T -----------------
+// A's core columns are placed at irregular (ascending) offsets on purpose, the way the BiLSTM
+// kernel strings hidden tiles together, so the per-MMA leading-byte-offset is exercised.
+__global__ void __launch_bounds__(128, 1)
+k_umma_selftest(const unsigned char* __restrict__ a_img, const unsigned char* __restrict__ b_img, int n, int kcols,
+                float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t sbase = smem_u32(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // A column kc lives at kc*2048, plus a 4 KB hole after every 13th column
+  auto acol = [](int kc) { return (uint32_t)(kc * TC_ACOL + (kc / 13) * 4096); };
+  const uint32_t b_off = acol(kcols) + 4096;
+  for (int kc = 0; kc < kcols; ++kc)
+    *reinterpret_cast<uint4*>(smem + acol(kc) + tid * 16) = *reinterpret_cast<const uint4*>(a_img + (size_t)kc * TC_ACOL + tid * 16);
+  fence_async_smem();
+  const uint32_t bfull = smem_u32(&bars[0]), bdone = smem_u32(&bars[1]);
+  if (tid == 0) {
+    mbar_init(bfull, 1);
+    mbar_init(bdone, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) tc_alloc(smem_u32(&tmem_slot));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const uint32_t bcol = (uint32_t)n * 16;
+  if (tid == 0) {
+    mbar_expect_tx(bfull, bcol * kcols);
+    bulk_g2s(sbase + b_off, b_img, bcol * kcols, bfull);
+    mbar_wait(bfull, 0);
+    tc_fence_after();
+    const uint32_t idesc = umma_idesc(128, n);
+    for (int k16 = 0; k16 < kcols / 2; ++k16) {
+      const uint32_t a0 = sbase + acol(2 * k16), a1 = sbase + acol(2 * k16 + 1);
+      tc_mma(tmem_base, umma_desc(a0, a1 - a0, 128), umma_desc(sbase + b_off + 2 * k16 * bcol, bcol, 128), idesc,
+             k16 > 0 ? 1u : 0u);
+    }
+    tc_commit(bdone);
+  }
+  mbar_wait(bdone, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < n; c0 += 16) {
+    uint32_t v[16];
+    tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tc_wait_ld();
+    for (int i = 0; i < 16; ++i) out[(size_t)(warp * 32 + lane) * n + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tc_dealloc(tmem_base); }
+}
+
+uint16_t h_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+float h_bf16f(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+}  // namespace
+
+// Host-side image of one (direction, layer) for the weight ring: [chunk j][core column kc][n 80][8 k]
+// bf16, n = 4*unit_in_chunk + gate.  K order (virtual operand columns):
+//   layer 0: col 0 = (A, C, G, T, mean_hi, stdv_hi, len_hi, len_lo); cols 1..13 = h0 tile
+//            (k 0..99 hidden, 100/101 bias hi/lo against the ones, 102 mean_lo, 103 stdv_lo)
+//   layer 1,2: cols 0..12 = tile of the layer below (100/101 carry this layer's bias),
+//            cols 13..25 = own hidden tile (extras unused).
+// The sigmoid gates (i, f, o) are pre-scaled by 0.5 because the epilogue evaluates
+// sigmoid(x) = 0.5*tanh(x/2)+0.5; forget_bias = 1.0 (BasicLSTMCell) is folded into the bias.
+void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, std::vector<uint16_t>& img) {
+  const int ncols = layer == 0 ? 14 : 26;
+  img.assign((size_t)TC_NCHUNK * ncols * TC_CHUNK_N * 8, 0);
+  for (int j = 0; j < TC_NCHUNK; ++j)
+    for (int kc = 0; kc < ncols; ++kc)
+      for (int n = 0; n < TC_CHUNK_N; ++n) {
+        const int unit = 20 * j + n / 4, gate = n % 4, col = gate * DM_HIDDEN + unit;
+        const float scale = gate == 1 ? 1.0f : 0.5f;
+        const float bsc = (bias[col] + (gate == 2 ? 1.0f : 0.0f)) * scale;
+        const uint16_t bhi = h_bf16(bsc), blo = h_bf16(bsc - h_bf16f(bhi));
+        for (int e = 0; e < 8; ++e) {
+          uint16_t val = 0;
+          auto wref = [&](int r) { return h_bf16(kernel[(size_t)r * DM_GATES + col] * scale); };
+          if (layer == 0) {
+            if (kc == 0) {
+              static const int xr[8] = {0, 1, 2, 3, 4, 5, 6, 6};
+              val = wref(xr[e]);
+            } else {
+              const int kk = (kc - 1) * 8 + e;
+              if (kk < DM_HIDDEN) val = wref(DM_FNUM + kk);
+              else if (kk == 100) val = bhi;
+              else if (kk == 101) val = blo;
+              else if (kk == 102) val = wref(4);
+              else val = wref(5);
+            }
+          } else {
+            if (kc < TC_HCOLS) {
+              const int kk = kc * 8 + e;
+              if (kk < DM_HIDDEN) val = wref(kk);
+              else if (kk == 100) val = bhi;
+              else if (kk == 101) val = blo;
+            } else {
+              const int kk = (kc - TC_HCOLS) * 8 + e;
+              if (kk < DM_HIDDEN) val = wref(DM_HIDDEN + kk);
+            }
+          }
+          img[(((size_t)j * ncols + kc) * TC_CHUNK_N + n) * 8 + e] = val;
+        }
+      }
+}
+
+static int tc_prepare(dm_ctx* ctx) {
+  if (!ctx->tc_attr_set) {
+    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DM_CUDA(ctx, cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ctx->tc_attr_set = true;
+  }
+  return DM_OK;
+}
+
+int dm_launch_lstm_tc(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_windows,
+                      float* p1, uint8_t* pred) {
+  const int64_t n_pad = dm_pad_windows(n_windows);
+  if (n_pad == 0) return DM_OK;
+  int rc = tc_prepare(ctx);
+  if (rc != DM_OK) return rc;
+  k_lstm_tc<<<(unsigned)(n_pad / DM_TILE_M), TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred,
+                                                                                 2 * TC_STEPS_PER_DIR, nullptr);
+  ctx->launches += 1;
+  DM_CUDA(ctx, cudaGetLastError());
+  return DM_OK;
+}
+
+// debug: run the first `max_steps` cell-steps of tile 0 and return its shared-memory operand
+// region (x columns + the five hidden tiles, OFF_W bytes)
+int dm_tc_debug(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_windows, float* p1,
+                uint8_t* pred, int max_steps, unsigned char* dump_host, int64_t dump_cap) {
+  const int64_t n_pad = dm_pad_windows(n_windows);
+  if (n_pad == 0) return DM_OK;
+  int rc = tc_prepare(ctx);
+  if (rc != DM_OK) return rc;
+  unsigned char* dbg = nullptr;
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dbg), OFF_W));
+  k_lstm_tc<<<(unsigned)(n_pad / DM_TILE_M), TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred,
+                                                                                 max_steps, dbg);
+  ctx->launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && dump_host)
+    e = cudaMemcpy(dump_host, dbg, (size_t)std::min<int64_t>(dump_cap, OFF_W), cudaMemcpyDeviceToHost);
+  cudaFree(dbg);
+  if (e != cudaSuccess) { dm_set_error(ctx, std::string("dm_tc_debug: ") + cudaGetErrorString(e)); return DM_ERR_CUDA; }
+  return DM_OK;
+}
+
+int dm_tc_selftest(dm_ctx* ctx, int n, int k, float* max_err) {
+  if (n < 16 || n > 256 || n % 16 || k < 16 || k > 416 || k % 16) {
+    dm_set_error(ctx, "dm_selftest_umma: need n in [16,256] and k in [16,416], both multiples of 16");
+    return DM_ERR_ARG;
+  }
+  int rc = tc_prepare(ctx);
+  if (rc != DM_OK) return rc;
+  const int kcols = k / 8;
+  std::vector<float> A((size_t)128 * k), B((size_t)n * k);
+  uint32_t s = 12345u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 32768.0f - 1.0f; };
+  for (auto& x : A) x = h_bf16f(h_bf16(rnd()));
+  for (auto& x : B) x = h_bf16f(h_bf16(rnd() * 4.0f));
+  std::vector<uint16_t> ai((size_t)kcols * 128 * 8), bi((size_t)kcols * n * 8);
+  for (int kc = 0; kc < kcols; ++kc)
+    for (int e = 0; e < 8; ++e) {
+      for (int r = 0; r < 128; ++r) ai[((size_t)kc * 128 + r) * 8 + e] = h_bf16(A[(size_t)r * k + kc * 8 + e]);
+      for (int c = 0; c < n; ++c) bi[((size_t)kc * n + c) * 8 + e] = h_bf16(B[(size_t)c * k + kc * 8 + e]);
+    }
+  unsigned char *a_d = nullptr, *b_d = nullptr;
+  float* o_d = nullptr;
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&a_d), ai.size() * 2));
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&b_d), bi.size() * 2));
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&o_d), sizeof(float) * 128 * n));
+  DM_CUDA(ctx, cudaMemcpy(a_d, ai.data(), ai.size() * 2, cudaMemcpyHostToDevice));
+  DM_CUDA(ctx, cudaMemcpy(b_d, bi.data(), bi.size() * 2, cudaMemcpyHostToDevice));
+  const size_t smem = (size_t)kcols * TC_ACOL + (kcols / 13 + 2) * 4096 + (size_t)kcols * n * 16;
+  if (smem > 200 * 1024) { dm_set_error(ctx, "dm_selftest_umma: n*k too large for one CTA"); return DM_ERR_ARG; }
+  k_umma_selftest<<<1, 128, smem, ctx->stream>>>(a_d, b_d, n, kcols, o_d);
+  ctx->launches += 1;
+  std::vector<float> out((size_t)128 * n);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(out.data(), o_d, out.size() * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(a_d); cudaFree(b_d); cudaFree(o_d);
+  if (e != cudaSuccess) { dm_set_error(ctx, std::string("dm_selftest_umma: ") + cudaGetErrorString(e)); return DM_ERR_CUDA; }
+  double worst = 0.0;
+  for (int r = 0; r < 128; ++r)
+    for (int c = 0; c < n; ++c) {
+      double ref = 0.0;
+      for (int kk = 0; kk < k; ++kk) ref += (double)A[(size_t)r * k + kk] * (double)B[(size_t)c * k + kk];
+      worst = std::max(worst, std::fabs(ref - (double)out[(size_t)r * n + c]));
+    }
+  *max_err = (float)worst;
+  return DM_OK;
+}

@@ -1,0 +1,163 @@
+/*
+ * deepmod_b200 -- C ABI of the B200-native DeepMod `detect` hot path.
+ *
+ * The reference (WGLab/DeepMod) is pure Python over TensorFlow 1.x and has no
+ * FFI of its own; the seams this library replaces are (paths relative to the
+ * reference tree):
+ *
+ *   - the session tuple  sp_options['rnn'] = (sess, X, Y, init_l, mfpred)
+ *       bin/DeepMod_scripts/myDetect.py:972, consumed at :805 and :816-820
+ *       -> dm_forward_windows()
+ *   - get_Feature()      bin/DeepMod_scripts/myDetect.py:839-903
+ *     mPredict1()        bin/DeepMod_scripts/myDetect.py:787-834
+ *       -> dm_detect_batch() (features, windows, BiLSTM, label write-back, and
+ *          the per-position accumulation of sum_handler :1089-1100, fused)
+ *   - sum_handler() BED writer  bin/DeepMod_scripts/myDetect.py:1107-1120
+ *       -> dm_hist_nonzero() / dm_write_bed()
+ *   - model restore      bin/DeepMod_scripts/myDetect.py:950-956
+ *       -> dm_create() takes the 14 restored tensors in the reference layout
+ *
+ * Conventions: plain pointers and sizes only; every pointer is HOST memory unless
+ * the name ends in _d; every function returns 0 on success or a negative dm_status
+ * and never throws.  A context is bound to one GPU and must be driven by one host
+ * thread at a time.  The library has no CPU fallback: without a CUDA device
+ * dm_create() fails with DM_ERR_CUDA.
+ */
+#ifndef DEEPMOD_B200_H
+#define DEEPMOD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DM_WINDOW   21   /* --windowsize default, bin/DeepMod.py:317 */
+#define DM_FNUM      7   /* --fnum default,       bin/DeepMod.py:318 */
+#define DM_HIDDEN  100   /* --hidden default,     bin/DeepMod.py:319 */
+#define DM_LIVE_STEPS 11 /* outputs[int(21/2)]: myMultiBiRNN.py:55  */
+
+typedef struct dm_ctx dm_ctx;
+
+enum dm_status {
+  DM_OK = 0,
+  DM_ERR_ARG = -1,
+  DM_ERR_CUDA = -2,
+  DM_ERR_STATE = -3,
+  DM_ERR_IO = -4
+};
+
+/* arithmetic of the BiLSTM */
+enum dm_precision {
+  DM_FP32 = 0,   /* fp32 FMA + accurate expf/tanhf: the parity path (<=1e-4 on p1) */
+  DM_BF16 = 1    /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM */
+};
+
+/* per-read status written by dm_detect_batch (mirrors sp_param['f5status']) */
+enum dm_read_status {
+  DM_READ_OK = 0,
+  DM_READ_MISMATCH = 1,    /* 'Error Does not match', myDetect.py:868-874 */
+  DM_READ_BAD_ALIGN = 2,   /* #non-gap columns != mapped events (reference would raise) */
+  DM_READ_LESS_EVENT = 3   /* 'Less Event', myDetect.py:702-705 */
+};
+
+/* The 14 inference tensors exactly as Saver.restore leaves them (fp32, row-major):
+ * kernel[d][0] is [107,400], kernel[d][1..2] are [200,400], bias[d][l] is [400];
+ * rows = [input | h], columns = [i | j | f | o] (BasicLSTMCell); d: 0 = fw, 1 = bw.
+ * cls_w is `Variable` [200,2] (rows = [fw h | bw h]), cls_b is `Variable_1` [2]. */
+typedef struct dm_weights {
+  const float* kernel[2][3];
+  const float* bias[2][3];
+  const float* cls_w;
+  const float* cls_b;
+} dm_weights;
+
+/* One packed batch of aligned reads (host pointers; see deepmod_b200/synth.py).
+ * Columns and clips are in READ orientation ('-' strand already flipped and
+ * complemented, myDetect.py:661-666). */
+typedef struct dm_batch {
+  int32_t        n_reads;
+  const int64_t* ev_off;       /* [n_reads+1] */
+  const float*   ev_mean;      /* [ev_off[n]] normalised mean,   myDetect.py:898 */
+  const float*   ev_stdv;      /*             normalised stdv,   :899 */
+  const float*   ev_len;       /*             raw-sample count,  :900 */
+  const uint8_t* ev_base;      /* ASCII k-mer centre (model_state[2]); NULL = skip the :868 check */
+  const int64_t* col_off;      /* [n_reads+1] */
+  const uint8_t* col_refbase;  /* ASCII, '-' = insertion */
+  const uint8_t* col_readbase; /* ASCII, '-' = deletion  */
+  const int64_t* col_refpos;   /* 0-based reference position of the column */
+  const int32_t* start_clip;   /* [n_reads] */
+  const int32_t* end_clip;     /* [n_reads] */
+  const int32_t* contig;       /* [n_reads] index into dm_set_genome's contigs */
+  const int8_t*  strand;       /* [n_reads] +1 / -1 */
+} dm_batch;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int  dm_create(dm_ctx** out, int device, const dm_weights* w, int precision);
+void dm_destroy(dm_ctx* ctx);
+const char* dm_last_error(const dm_ctx* ctx);   /* ctx may be NULL: last global error */
+int  dm_version(void);
+/* pick the arithmetic of subsequent calls (both weight images are always resident) */
+int  dm_set_precision(dm_ctx* ctx, int precision);
+
+/* ---- model only (b1 seam) ---------------------------------------------- */
+/* X is [n,21,7] fp32 windows as mPredict1 builds them (:791-803).  p1_out[n]
+ * receives softmax(logits)[:,1]; pred_out[n] receives argmax (what `mfpred`
+ * fetches, myMultiBiRNN.py:61).  Either output may be NULL. */
+int dm_forward_windows(dm_ctx* ctx, int64_t n, const float* X, float* p1_out, uint8_t* pred_out);
+
+/* ---- per-position accumulator (sum_handler's dict) ----------------------- */
+/* Allocates and zeroes one (cov, mod, del) cell per reference position and strand
+ * for `base` (the --Base of interest, bin/DeepMod.py:331). */
+int dm_set_genome(dm_ctx* ctx, int32_t n_contigs, const int64_t* contig_len, char base);
+int dm_hist_clear(dm_ctx* ctx);
+/* Device pointer + length (in uint64 cells) of the whole accumulator, for the one
+ * end-of-job NCCL sum across GPUs (each cell packs three 21-bit counters, so a
+ * sum of cells is the sum of counters). */
+int dm_hist_device_ptr(dm_ctx* ctx, void** cells_d, int64_t* n_cells);
+/* Rows that exist in the reference's dict for (contig, strand): positions touched
+ * by at least one alignment column whose refbase == base (deletions included,
+ * myDetect.py:1093-1094), ascending.  Call with pos == NULL to get the count. */
+int dm_hist_nonzero(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t cap,
+                    int64_t* pos, int32_t* cov, int32_t* mod, int64_t* n_rows);
+/* Writes mod_pos.<chr><strand>.<Base>.bed in sum_handler's exact text format
+ * (myDetect.py:1116-1120).  No file is created when there are no rows (:1109). */
+int dm_write_bed(dm_ctx* ctx, int32_t contig, int8_t strand, const char* chrom,
+                 const char* path, int64_t* n_rows);
+
+/* ---- the hot path ------------------------------------------------------- */
+/* get_Feature + mPredict1 + reducer for a packed batch, host buffers in, host
+ * results out.  p1_out / pred_out are indexed by window (= mapped event), reads
+ * concatenated in order, sum(Lmap) entries; windows of rejected reads hold 0.
+ * status_out[n_reads] receives dm_read_status.  Any output may be NULL. */
+int dm_detect_batch(dm_ctx* ctx, const dm_batch* b, float* p1_out, uint8_t* pred_out,
+                    int32_t* status_out);
+
+/* Same work with the batch resident in HBM: upload once, run many times. */
+int dm_batch_upload(dm_ctx* ctx, const dm_batch* b, int64_t* n_windows);
+int dm_detect_resident(dm_ctx* ctx, int accumulate /* 0: skip the histogram update */);
+int dm_fetch_results(dm_ctx* ctx, float* p1_out, uint8_t* pred_out, int32_t* status_out);
+
+/* Materialise the [sum(Lmap),21,7] fp32 windows of the uploaded batch exactly as
+ * mPredict1 slices them (:791-803) -- parity hook for the gather kernel. */
+int dm_build_windows(dm_ctx* ctx, float* windows_out);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* Number of kernels this library launched since creation, and device time of the
+ * BiLSTM kernels of the last dm_detect_* call (CUDA events on the library's stream). */
+int64_t dm_launch_count(const dm_ctx* ctx);
+int dm_last_timing(const dm_ctx* ctx, float* lstm_ms, float* total_ms);
+/* tcgen05 descriptor/layout self-test: one 128 x n x k bf16 GEMM through the same
+ * UMMA + TMEM path the BiLSTM uses; returns max |err| vs fp32 in *max_err. */
+int dm_selftest_umma(dm_ctx* ctx, int n, int k, float* max_err);
+/* Debug hook of the tensor-core BiLSTM: run only the first `max_steps` (1..66) cell-steps
+ * (wavefront order, fw then bw) on windows X[n,21,7] and copy the first tile's operand
+ * region of shared memory (2 x-columns + 5 hidden tiles, 137216 bytes, UMMA canonical
+ * K-major layout) into `dump`.  p1_out[n] is only meaningful for max_steps == 66. */
+int dm_debug_tc_windows(dm_ctx* ctx, int64_t n, const float* X, int max_steps, uint8_t* dump,
+                        int64_t dump_cap, float* p1_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPMOD_B200_H */
