@@ -172,7 +172,8 @@ __global__ void k_feature_rows(int n_reads, int64_t n_frows, const int64_t* __re
       f[4] = ev_mean[e];
       f[5] = ev_stdv[e];
       f[6] = ev_len[e];
-      if (ie >= sc && ie < L - ec) {
+      // reads with fewer than 50 mapped events own no windows (and no win_col entries)
+      if (ie >= sc && ie - sc < win_off[r + 1] - win_off[r]) {
         int64_t c = win_col[win_off[r] + (ie - sc)];
         if (c >= 0) {
           uint8_t b = refbase[c];

@@ -310,6 +310,13 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             lows = make_uint2(0x3F803F80u, 0u);     // (1, 1, 0, 0): bias carriers for layer 2
           }
           const uint32_t htile = l == 0 ? OFF_H0 + (t & 1) * TC_HTILE : l == 1 ? OFF_H1 + (t & 1) * TC_HTILE : OFF_H2;
+          if (l == 2) {
+            // h2 is single-buffered: its old value is an operand of ALL five chunks of this very
+            // step, so nothing may be written before the last chunk's MMAs have retired
+            uint32_t s4 = tslot + (TC_NCHUNK - 1), u4 = tuse;
+            if (s4 >= TC_TSLOTS) { s4 -= TC_TSLOTS; ++u4; }
+            mbar_wait(bar0 + 8 * (BAR_TFULL + s4), u4 & 1);
+          }
 #pragma unroll
           for (int j = 0; j < TC_NCHUNK; ++j) {
             mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);

@@ -28,7 +28,7 @@ def golden_batch():
     return z, names, lens
 
 
-@pytest.fixture(scope="session", params=MODEL_TAGS)
+@pytest.fixture(params=MODEL_TAGS)
 def model_tag(request):
     return request.param
 

@@ -1,0 +1,182 @@
+"""Parity of the CUDA path against the oracle / golden fixtures, through the C ABI (B200 only)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_model, golden_reads, golden_windows
+
+pytestmark = pytest.mark.gpu
+
+P1_TOL = 1e-4          # BASELINE.json north_star: per-base probabilities within 1e-4 (fp32 path)
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from deepmod_b200 import capi
+    capi.load_library()
+    return capi
+
+
+def make_ctx(capi, tag, precision=0):
+    from deepmod_b200 import checkpoint
+    return capi.Context(checkpoint.Model.from_dict(golden_model(tag)), device=0, precision=precision)
+
+
+def test_forward_windows_fp32(capi, model_tag):
+    g = golden_windows(model_tag)
+    with make_ctx(capi, model_tag) as ctx:
+        p1, pred = ctx.forward_windows(g["X"])
+        assert ctx.launches >= 2
+    err = np.abs(p1.astype(np.float64) - g["p1"])
+    assert err.max() <= P1_TOL, err.max()
+    safe = np.abs(g["p1"] - 0.5) > P1_TOL
+    assert np.array_equal(pred[safe], g["pred"][safe])
+    print("fp32 max |dp1| = %.3g" % err.max())
+
+
+def test_forward_windows_ragged_sizes(capi):
+    g = golden_windows("conmodC_P100")
+    with make_ctx(capi, "conmodC_P100") as ctx:
+        for n in (1, 63, 64, 65, 127, 129, 500):
+            p1, pred = ctx.forward_windows(g["X"][:n])
+            assert np.abs(p1 - g["p1"][:n]).max() <= P1_TOL
+        p1, pred = ctx.forward_windows(g["X"][:0])
+        assert len(p1) == 0
+
+
+def test_window_gather_bit_exact(capi, golden_batch):
+    """get_Feature + the window slicing of mPredict1 (myDetect.py:791-803, :839-903)."""
+    from oracle import detect_ref
+    batch, names, lens = golden_batch
+    with make_ctx(capi, "conmodC_P100") as ctx:
+        n = ctx.upload(batch)
+        got = ctx.build_windows(n)
+    want = []
+    for r in range(len(batch["start_clip"])):
+        rd = detect_ref.unpack_read(batch, r)
+        L = len(rd["ev_mean"])
+        if L - rd["start_clip"] - rd["end_clip"] < 50:
+            continue
+        mf, st = detect_ref.get_feature(rd["ev_mean"], rd["ev_stdv"], rd["ev_len"], rd["ev_base"], rd["refbase"],
+                                        rd["readbase"], rd["start_clip"], rd["end_clip"])
+        win = detect_ref.windows_from_features(mf, L, rd["start_clip"], rd["end_clip"])
+        if st != detect_ref.STATUS_OK:
+            # the reference never builds windows for a rejected read; only the layout is compared
+            win = None
+        want.append(win)
+    # compare read by read using the per-read window counts
+    from deepmod_b200.capi import PackedBatch
+    counts = PackedBatch(batch).n_windows_per_read
+    wi = 0
+    off = 0
+    for r, c in enumerate(counts):
+        if c == 0:
+            continue
+        w = want[wi]; wi += 1
+        if w is not None:
+            assert np.array_equal(got[off:off + c], w.astype(np.float32)), "read %d" % r
+        off += c
+    assert off == n
+
+
+def _check_reads(capi, tag, batch, names, lens, precision, tmp_path):
+    g = golden_reads(tag)
+    with make_ctx(capi, tag, precision) as ctx:
+        ctx.set_genome(lens, g["base"])
+        p1, pred, status = ctx.detect_batch(batch)
+        assert list(status) == list(g["status"])
+        pb = capi.PackedBatch(batch)
+        ok = np.repeat(status == 0, pb.n_windows_per_read)
+        beds = {}
+        for ci, name in enumerate(names):
+            for s in "+-":
+                path = os.path.join(str(tmp_path), "mod_pos.%s%s.%s.bed" % (name, s, g["base"]))
+                if ctx.write_bed(ci, s, name, path):
+                    beds[name + s] = open(path).read()
+        hist = {(ci, s): ctx.hist_nonzero(ci, s) for ci in range(len(names)) for s in "+-"}
+    assert np.all(p1[~ok] == 0) and np.all(pred[~ok] == 0)
+    return p1[ok], pred[ok], beds, hist, g
+
+
+def test_detect_batch_fp32_matches_reference(capi, model_tag, golden_batch, tmp_path):
+    batch, names, lens = golden_batch
+    p1, pred, beds, hist, g = _check_reads(capi, model_tag, batch, names, lens, 0, tmp_path)
+    err = np.abs(p1.astype(np.float64) - g["p1"])
+    assert err.max() <= P1_TOL, err.max()
+    assert np.array_equal(pred, g["pred"])            # counts bit-exact
+    assert beds == g["bed"]                            # BED text byte-for-byte
+    # hist_nonzero agrees with the BED rows
+    for key, text in g["bed"].items():
+        rows = [ln.split(" ") for ln in text.splitlines()]
+        ci = names.index(key[:-1])
+        pos, cov, mod = hist[(ci, key[-1])]
+        assert [int(r[1]) for r in rows] == list(pos)
+        assert [int(r[9]) for r in rows] == list(cov)
+        assert [int(r[11]) for r in rows] == list(mod)
+
+
+def test_accumulate_is_additive_and_clearable(capi, golden_batch):
+    batch, names, lens = golden_batch
+    with make_ctx(capi, "conmodC_P100") as ctx:
+        ctx.set_genome(lens, "C")
+        ctx.detect_batch(batch)
+        a = ctx.hist_nonzero(0, "+")
+        ctx.detect_batch(batch)
+        b = ctx.hist_nonzero(0, "+")
+        assert np.array_equal(a[0], b[0]) and np.array_equal(2 * a[1], b[1]) and np.array_equal(2 * a[2], b[2])
+        ctx.hist_clear()
+        c = ctx.hist_nonzero(0, "+")
+        assert len(c[0]) == 0
+        # split the batch in two calls: same accumulator as one call
+        from deepmod_b200 import synth
+        ctx.detect_batch(synth.take_reads(batch, np.arange(0, 5)))
+        ctx.detect_batch(synth.take_reads(batch, np.arange(5, 10)))
+        d = ctx.hist_nonzero(0, "+")
+        assert all(np.array_equal(x, y) for x, y in zip(a, d))
+
+
+def test_empty_and_rejected_only_batches(capi, golden_batch):
+    from deepmod_b200 import synth
+    batch, names, lens = golden_batch
+    with make_ctx(capi, "conmodC_P100") as ctx:
+        ctx.set_genome(lens, "C")
+        p1, pred, status = ctx.detect_batch(synth.take_reads(batch, np.arange(0, 0)))
+        assert len(p1) == 0 and len(status) == 0
+        p1, pred, status = ctx.detect_batch(synth.take_reads(batch, np.array([0])))      # Less Event
+        assert list(status) == [3] and len(p1) == 0
+        p1, pred, status = ctx.detect_batch(synth.take_reads(batch, np.array([8])))      # Does not match
+        assert list(status) == [1] and np.all(pred == 0)
+        assert all(len(ctx.hist_nonzero(ci, s)[0]) == 0 for ci in range(len(names)) for s in "+-")
+
+
+def test_umma_selftest(capi):
+    """tcgen05 descriptors / TMEM / bulk copy: one bf16 GEMM against fp64."""
+    with make_ctx(capi, "conmodC_P100", 1) as ctx:
+        for n, k in ((80, 112), (80, 208), (16, 16), (256, 64)):
+            err = ctx.selftest_umma(n, k)
+            assert err < 2e-3 * np.sqrt(k), (n, k, err)
+
+
+def test_forward_windows_bf16(capi, model_tag):
+    """bf16 tensor-core path: not a 1e-4 path; bounded error + reported flip rate."""
+    g = golden_windows(model_tag)
+    with make_ctx(capi, model_tag, 1) as ctx:
+        p1, pred = ctx.forward_windows(g["X"])
+    err = np.abs(p1.astype(np.float64) - g["p1"])
+    flips = float(np.mean(pred != g["pred"]))
+    print("bf16 %s: max |dp1| %.3g mean %.3g flip rate %.4f" % (model_tag, err.max(), err.mean(), flips))
+    assert err.mean() < 0.01 and flips < 0.02 and np.quantile(err, 0.99) < 0.1
+
+
+def test_detect_batch_bf16_close(capi, golden_batch, tmp_path):
+    batch, names, lens = golden_batch
+    p1, pred, beds, hist, g = _check_reads(capi, "conmodC_P100", batch, names, lens, 1, tmp_path)
+    flips = float(np.mean(pred != g["pred"]))
+    print("bf16 reads: flip rate %.4f, mean |dp1| %.3g" % (flips, np.abs(p1 - g["p1"]).mean()))
+    assert flips < 0.02
+    # coverage does not depend on the model: bit-exact even on the bf16 path
+    for key, text in g["bed"].items():
+        rows = [ln.split(" ") for ln in text.splitlines()]
+        pos, cov, mod = hist[(names.index(key[:-1]), key[-1])]
+        assert [int(r[1]) for r in rows] == list(pos) and [int(r[9]) for r in rows] == list(cov)
