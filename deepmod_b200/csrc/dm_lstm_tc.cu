@@ -43,7 +43,7 @@ constexpr int TC_HTILE = TC_HCOLS * TC_ACOL;
 constexpr int TC_BCOL = TC_CHUNK_N * 16;   // B core column of one chunk: 80 n x 16 B
 constexpr int TC_STAGE_COLS = 14;
 constexpr int TC_STAGE = TC_STAGE_COLS * TC_BCOL;
-constexpr int TC_NSTAGE = 4;
+constexpr int TC_NSTAGE = 5;
 constexpr int TC_STEPS_PER_DIR = 33;
 
 constexpr int OFF_X = 0;                                   // 2 x-columns
@@ -52,7 +52,7 @@ constexpr int OFF_H1 = OFF_H0 + 2 * TC_HTILE;              // h1[2]
 constexpr int OFF_H2 = OFF_H1 + 2 * TC_HTILE;              // h2
 constexpr int OFF_W = OFF_H2 + TC_HTILE;                   // weight ring
 constexpr int OFF_BAR = OFF_W + TC_NSTAGE * TC_STAGE;
-constexpr int BAR_FULL = 0, BAR_EMPTY = 4, BAR_TFULL = 8, BAR_TEMPTY = 14, BAR_HDONE = 20, N_BARS = 22;
+constexpr int BAR_FULL = 0, BAR_EMPTY = 5, BAR_TFULL = 10, BAR_TEMPTY = 16, BAR_HDONE = 22, N_BARS = 24;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int OFF_PART = OFF_TMEM + 16;                    // float part[5][128]
 constexpr int OFF_FROW = OFF_PART + 5 * 128 * 4;           // int frow[128]
@@ -220,7 +220,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             const int ncols = l == 0 ? 14 : 26;
             for (int j = 0; j < TC_NCHUNK; ++j) {
               for (int half = 0; half < (l == 0 ? 1 : 2); ++half) {
-                const uint32_t slot = st & (TC_NSTAGE - 1), use = st / TC_NSTAGE;
+                const uint32_t slot = st % TC_NSTAGE, use = st / TC_NSTAGE;
                 if (use > 0) mbar_wait(bar0 + 8 * (BAR_EMPTY + slot), (use - 1) & 1);
                 const uint32_t bytes = (half == 0 ? 14 : 12) * TC_BCOL;
                 mbar_expect_tx(bar0 + 8 * (BAR_FULL + slot), bytes);
@@ -259,7 +259,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
               const uint32_t d_tmem = tmem_base + tslot * TC_CHUNK_N;
               int k16 = 0;
               for (int half = 0; half < (l == 0 ? 1 : 2); ++half) {
-                const uint32_t slot = st & (TC_NSTAGE - 1), use = st / TC_NSTAGE;
+                const uint32_t slot = st % TC_NSTAGE, use = st / TC_NSTAGE;
                 mbar_wait(bar0 + 8 * (BAR_FULL + slot), use & 1);
                 tc_fence_after();
                 const uint32_t wb = sbase + OFF_W + slot * TC_STAGE;
@@ -310,13 +310,9 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             lows = make_uint2(0x3F803F80u, 0u);     // (1, 1, 0, 0): bias carriers for layer 2
           }
           const uint32_t htile = l == 0 ? OFF_H0 + (t & 1) * TC_HTILE : l == 1 ? OFF_H1 + (t & 1) * TC_HTILE : OFF_H2;
-          if (l == 2) {
-            // h2 is single-buffered: its old value is an operand of ALL five chunks of this very
-            // step, so nothing may be written before the last chunk's MMAs have retired
-            uint32_t s4 = tslot + (TC_NCHUNK - 1), u4 = tuse;
-            if (s4 >= TC_TSLOTS) { s4 -= TC_TSLOTS; ++u4; }
-            mbar_wait(bar0 + 8 * (BAR_TFULL + s4), u4 & 1);
-          }
+          // h2 is single-buffered and its old value is an operand of ALL five chunks of this very
+          // step: layer 2 keeps its new h in registers until the last chunk's MMAs have retired
+          uint32_t hkeep[TC_NCHUNK][2];
 #pragma unroll
           for (int j = 0; j < TC_NCHUNK; ++j) {
             mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
@@ -354,8 +350,21 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             const int u0 = 20 * j + 4 * sgrp;
             unsigned char* dst = smem + htile + (u0 >> 3) * TC_ACOL + row_off + (u0 & 7) * 2;
             const uint32_t h01 = pack_bf16(hn[0], hn[1]), h23 = pack_bf16(hn[2], hn[3]);
-            if (j == TC_NCHUNK - 1 && sgrp == 4) *reinterpret_cast<uint4*>(dst) = make_uint4(h01, h23, lows.x, lows.y);
-            else *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
+            if (l == 2) {
+              hkeep[j][0] = h01; hkeep[j][1] = h23;
+              if (j == TC_NCHUNK - 1) {
+#pragma unroll
+                for (int jj = 0; jj < TC_NCHUNK; ++jj) {
+                  const int uu = 20 * jj + 4 * sgrp;
+                  *reinterpret_cast<uint2*>(smem + htile + (uu >> 3) * TC_ACOL + row_off + (uu & 7) * 2) =
+                      make_uint2(hkeep[jj][0], hkeep[jj][1]);
+                }
+              }
+            } else if (j == TC_NCHUNK - 1 && sgrp == 4) {
+              *reinterpret_cast<uint4*>(dst) = make_uint4(h01, h23, lows.x, lows.y);
+            } else {
+              *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
+            }
           }
           if (l == 0 && sgrp == 0 && t + 2 <= 10)
             *reinterpret_cast<uint4*>(smem + OFF_X + (t & 1) * TC_ACOL + row_off) = xnext;
