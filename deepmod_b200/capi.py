@@ -11,13 +11,13 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdeepmod_b200.so")
 
-FP32, BF16 = 0, 1
+FP32, BF16, BF16_1CTA = 0, 1, 2
 READ_OK, READ_MISMATCH, READ_BAD_ALIGN, READ_LESS_EVENT = 0, 1, 2, 3
 STATUS_TEXT = {READ_OK: "", READ_MISMATCH: "Error Does not match",      # myDetect.py:870
                READ_BAD_ALIGN: "Error alignment/event count mismatch",
                READ_LESS_EVENT: "Less Event"}                           # myDetect.py:704
 WINDOW, FNUM, HIDDEN = 21, 7, 100
-TC_DUMP_BYTES = 137216
+TC_DUMP_BYTES = 137216 + 8 * 8192
 
 _fp = C.POINTER(C.c_float)
 _i64p = C.POINTER(C.c_int64)

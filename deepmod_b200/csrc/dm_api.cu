@@ -71,7 +71,7 @@ void pack_fp32(const float* kernel, const float* bias, int layer, std::vector<fl
 
 }  // namespace
 
-void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, std::vector<uint16_t>& img);  // dm_lstm_tc.cu
+void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool pair, std::vector<uint16_t>& img);  // dm_lstm_tc.cu
 
 void dm_set_error(dm_ctx* ctx, const std::string& msg) {
   g_error = msg;
@@ -87,7 +87,7 @@ const char* dm_last_error(const dm_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 int dm_create(dm_ctx** out, int device, const dm_weights* w, int precision) {
   if (!out || !w) return fail(nullptr, DM_ERR_ARG, "dm_create: null argument");
   *out = nullptr;
-  if (precision != DM_FP32 && precision != DM_BF16) return fail(nullptr, DM_ERR_ARG, "dm_create: bad precision");
+  if (precision != DM_FP32 && precision != DM_BF16 && precision != DM_BF16_1CTA) return fail(nullptr, DM_ERR_ARG, "dm_create: bad precision");
   for (int d = 0; d < 2; ++d)
     for (int l = 0; l < 3; ++l)
       if (!w->kernel[d][l] || !w->bias[d][l]) return fail(nullptr, DM_ERR_ARG, "dm_create: missing weight tensor");
@@ -106,7 +106,8 @@ int dm_create(dm_ctx** out, int device, const dm_weights* w, int precision) {
                                           std::to_string(prop.major) + std::to_string(prop.minor));
   dm_ctx* ctx = new dm_ctx();
   ctx->device = device;
-  ctx->precision = precision;
+  ctx->precision = precision == DM_FP32 ? DM_FP32 : DM_BF16;
+  ctx->tc_pair = precision != DM_BF16_1CTA;
   ctx->sm_count = prop.multiProcessorCount;
   auto bail = [&](int rc) { std::string m = ctx->err; dm_destroy(ctx); g_error = m; return rc; };
 #define DM_CK(call)                                                                         \
@@ -129,9 +130,12 @@ int dm_create(dm_ctx** out, int device, const dm_weights* w, int precision) {
       DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.b32[d][l]), B.size() * sizeof(float)));
       DM_CK(cudaMemcpy(ctx->w.w32[d][l], W.data(), W.size() * sizeof(float), cudaMemcpyHostToDevice));
       DM_CK(cudaMemcpy(ctx->w.b32[d][l], B.data(), B.size() * sizeof(float), cudaMemcpyHostToDevice));
-      dm_tc_pack_weights(w->kernel[d][l], w->bias[d][l], l, T);
+      dm_tc_pack_weights(w->kernel[d][l], w->bias[d][l], l, false, T);
       DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.wtc[d][l]), T.size() * sizeof(uint16_t)));
       DM_CK(cudaMemcpy(ctx->w.wtc[d][l], T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      dm_tc_pack_weights(w->kernel[d][l], w->bias[d][l], l, true, T);
+      DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.wtc2[d][l]), T.size() * sizeof(uint16_t)));
+      DM_CK(cudaMemcpy(ctx->w.wtc2[d][l], T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
   DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.cls_w), 2 * DM_HIDDEN * 2 * sizeof(float)));
   DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.cls_b), 2 * sizeof(float)));
@@ -156,6 +160,7 @@ void dm_destroy(dm_ctx* ctx) {
       cudaFree(ctx->w.w32[d][l]);
       cudaFree(ctx->w.b32[d][l]);
       cudaFree(ctx->w.wtc[d][l]);
+      cudaFree(ctx->w.wtc2[d][l]);
     }
   cudaFree(ctx->w.cls_w); cudaFree(ctx->w.cls_b); cudaFree(ctx->w.cls_d);
   dm_dev_batch* bs[2] = {&ctx->b, &ctx->fw};
@@ -181,8 +186,9 @@ void dm_destroy(dm_ctx* ctx) {
 
 int dm_set_precision(dm_ctx* ctx, int precision) {
   if (!ctx) return DM_ERR_ARG;
-  if (precision != DM_FP32 && precision != DM_BF16) return fail(ctx, DM_ERR_ARG, "dm_set_precision: bad precision");
-  ctx->precision = precision;
+  if (precision != DM_FP32 && precision != DM_BF16 && precision != DM_BF16_1CTA) return fail(ctx, DM_ERR_ARG, "dm_set_precision: bad precision");
+  ctx->precision = precision == DM_FP32 ? DM_FP32 : DM_BF16;
+  if (precision != DM_FP32) ctx->tc_pair = precision != DM_BF16_1CTA;
   return DM_OK;
 }
 

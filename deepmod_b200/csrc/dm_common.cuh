@@ -45,7 +45,8 @@ struct dm_dev_weights {
   float* b32[2][3];        // fp32 bias    [400]
   float* cls_w;            // [200][2]
   float* cls_b;            // [2]
-  __nv_bfloat16* wtc[2][3];  // tensor-core images (see above)
+  __nv_bfloat16* wtc[2][3];  // tensor-core images, one CTA per tile (see dm_lstm_tc.cu)
+  __nv_bfloat16* wtc2[2][3]; // tensor-core images split by CTA of a pair (cta_group::2)
   float* cls_d;            // [2][100] cls_w[:,1]-cls_w[:,0] per direction
   float cls_db;            // cls_b[1]-cls_b[0]
 };
@@ -101,6 +102,7 @@ struct dm_ctx {
   int64_t launches = 0;
   float lstm_ms = 0.f, total_ms = 0.f;
   bool fp32_attr_set = false, tc_attr_set = false;
+  bool tc_pair = true;            // CTA-pair (cta_group::2) variant of the tensor-core kernel
   std::string err;
 };
 
@@ -134,4 +136,5 @@ int dm_tc_debug(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_fr
 int dm_launch_windows_to_rows(dm_ctx* ctx, const float* X_d, int64_t n, float* feat,
                               __nv_bfloat16* feat_tc, int32_t* win_frow);   // dm_features.cu
 
-static inline int64_t dm_pad_windows(int64_t n) { return (n + DM_TILE_M - 1) / DM_TILE_M * DM_TILE_M; }
+// result buffers are padded to whole CTA pairs (2 x 128 windows)
+static inline int64_t dm_pad_windows(int64_t n) { return (n + 2 * DM_TILE_M - 1) / (2 * DM_TILE_M) * (2 * DM_TILE_M); }

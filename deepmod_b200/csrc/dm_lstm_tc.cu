@@ -30,8 +30,11 @@
 
 namespace {
 
-constexpr int TC_CTRL_WARPS = 4;        // 0: weight producer, 1: MMA issuer, 2: TMEM alloc, 3: idle
-constexpr int TC_EPI_WARPS = 20;        // 4 lane quarters x 5 column groups
+constexpr int TC_CTRL_WARPS = 4;        // warps 20..23: weight producer, MMA issuer, TMEM alloc, pair relay
+constexpr int TC_EPI_WARPS = 20;        // warps 0..19: 4 lane quarters x 5 column groups
+// The control warps carry the HIGHEST warp ids on purpose: the SM's issue arbiter favours high warp
+// ids, and a starved MMA issuer / weight producer stalls all 20 epilogue warps.
+constexpr int W_PROD = TC_EPI_WARPS, W_MMA = TC_EPI_WARPS + 1, W_ALLOC = TC_EPI_WARPS + 2, W_RELAY = TC_EPI_WARPS + 3;
 constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = (TC_CTRL_WARPS + TC_EPI_WARPS) * 32;
 constexpr int TC_CHUNK_N = 80;          // gate columns per MMA and TMEM slot
@@ -40,18 +43,27 @@ constexpr int TC_TSLOTS = 6;
 constexpr int TC_ACOL = 2048;           // A core column: 128 rows x 16 B
 constexpr int TC_HCOLS = 13;            // 100 units + 4 extra K slots
 constexpr int TC_HTILE = TC_HCOLS * TC_ACOL;
-constexpr int TC_BCOL = TC_CHUNK_N * 16;   // B core column of one chunk: 80 n x 16 B
-constexpr int TC_STAGE_COLS = 14;
-constexpr int TC_STAGE = TC_STAGE_COLS * TC_BCOL;
-constexpr int TC_NSTAGE = 5;
 constexpr int TC_STEPS_PER_DIR = 33;
+constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand dump
+
+// Geometry of the weight stream: one stage = the B operand of one N-chunk (all K core columns).
+// PAIR = two CTAs of a cluster drive ONE tcgen05.mma.cta_group::2 (M = 256, 128 windows each): every
+// CTA stages only its half of the gate columns (40 of the chunk's 80), so the per-SM L2 stream halves
+// and the ring holds a whole cell-step ahead of the tensor pipe.
+template <bool PAIR> struct Geo {
+  static constexpr int BCOL = (PAIR ? TC_CHUNK_N / 2 : TC_CHUNK_N) * 16;   // bytes of one B core column per CTA
+  static constexpr int STAGE = 26 * BCOL;                                  // 16640 / 33280
+  static constexpr int NSTAGE = PAIR ? 5 : 2;
+  static constexpr int NCTA = PAIR ? 2 : 1;
+};
+constexpr int TC_RING = 5 * 26 * 640;    // 83200 >= 2 * 33280
 
 constexpr int OFF_X = 0;                                   // 2 x-columns
 constexpr int OFF_H0 = OFF_X + 2 * TC_ACOL;                // h0[2]
 constexpr int OFF_H1 = OFF_H0 + 2 * TC_HTILE;              // h1[2]
 constexpr int OFF_H2 = OFF_H1 + 2 * TC_HTILE;              // h2
 constexpr int OFF_W = OFF_H2 + TC_HTILE;                   // weight ring
-constexpr int OFF_BAR = OFF_W + TC_NSTAGE * TC_STAGE;
+constexpr int OFF_BAR = OFF_W + TC_RING;
 constexpr int BAR_FULL = 0, BAR_EMPTY = 5, BAR_TFULL = 10, BAR_TEMPTY = 16, BAR_HDONE = 22, N_BARS = 24;
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int OFF_PART = OFF_TMEM + 16;                    // float part[5][128]
@@ -66,15 +78,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// try_wait suspends the thread in hardware (up to the hint, in ns) instead of spinning on the issue port
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
+      ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -115,6 +128,52 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// ---- CTA-pair (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(bar), "r"(rank) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}"
+      ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ void tc_commit2(uint32_t bar) {     // both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_alloc2(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_dst) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_dealloc2(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
 // UMMA shared-memory descriptor, K-major, no swizzle: 8-row core matrices of 128 contiguous
@@ -144,13 +203,28 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 __device__ __forceinline__ int tau_row(int dir, int tau) { return dir == 0 ? tau : DM_WINDOW - 1 - tau; }
 
 // ---- the kernel -----------------------------------------------------------------------------
+// Roles (warp ids): 0..19 epilogue; 20 weight producer; 21 MMA issuer (leader CTA) / accumulator-
+// drained relay (peer CTA); 22 TMEM allocator / hidden-state-written relay (peer); 23 stage-landed
+// relay (peer).  The relays exist because a cluster-scope release-arrive costs ~1000 cycles: the
+// peer's 20 epilogue warps arrive on cheap CTA-local barriers and ONE thread forwards each phase.
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__ win_frow, dm_dev_weights w,
           float* __restrict__ p1_out, uint8_t* __restrict__ pred_out, int max_steps, unsigned char* __restrict__ dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + OFF_BAR;
+  using G = Geo<PAIR>;
+  // development switches ride in the upper bits of max_steps (see dm_debug_tc_windows):
+  //   0x100 epilogue skips the gate math, 0x200 no tcgen05.mma is issued, 0x400 no weight loads
+  const bool dbg_nomath = (max_steps & 0x100) != 0, dbg_nomma = (max_steps & 0x200) != 0, dbg_noload = (max_steps & 0x400) != 0;
+  max_steps &= 0xFF;
+  // optional timeline of CTA 0 behind the operand dump: [role][step][slot] SM clocks
+  unsigned long long* ts = (dbg != nullptr && blockIdx.x == 0) ? reinterpret_cast<unsigned long long*>(dbg + OFF_W) : nullptr;
+#define TS(idx) do { if (ts) ts[(idx)] = clock64(); } while (0)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t crank = PAIR ? cluster_rank() : 0u;      // 0 = leader (issues the MMAs of the pair)
+  const bool leader = crank == 0;
   const int64_t win0 = (int64_t)blockIdx.x * DM_TILE_M;
   int* s_frow = reinterpret_cast<int*>(smem + OFF_FROW);
   float* s_part = reinterpret_cast<float*>(smem + OFF_PART);
@@ -161,25 +235,32 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   if (tid < DM_TILE_M) s_frow[tid] = win_frow[win0 + tid];
   if (tid < 200) s_cls[tid] = w.cls_d[tid];
   if (tid == 0) {
-    for (int i = 0; i < TC_NSTAGE; ++i) { mbar_init(bar0 + 8 * (BAR_FULL + i), 1); mbar_init(bar0 + 8 * (BAR_EMPTY + i), 1); }
-    for (int i = 0; i < TC_TSLOTS; ++i) { mbar_init(bar0 + 8 * (BAR_TFULL + i), 1); mbar_init(bar0 + 8 * (BAR_TEMPTY + i), TC_EPI_WARPS); }
-    mbar_init(bar0 + 8 * (BAR_HDONE + 0), TC_EPI_WARPS);
-    mbar_init(bar0 + 8 * (BAR_HDONE + 1), TC_EPI_WARPS);
+    // leader barriers also collect one forwarded arrival per phase from the peer CTA
+    const uint32_t extra = (PAIR && leader) ? 1 : 0;
+    for (int i = 0; i < G::NSTAGE; ++i) {
+      mbar_init(bar0 + 8 * (BAR_FULL + i), 1 + extra);
+      mbar_init(bar0 + 8 * (BAR_EMPTY + i), 1);
+    }
+    for (int i = 0; i < TC_TSLOTS; ++i) {
+      mbar_init(bar0 + 8 * (BAR_TFULL + i), 1);
+      mbar_init(bar0 + 8 * (BAR_TEMPTY + i), TC_EPI_WARPS + extra);
+    }
+    mbar_init(bar0 + 8 * (BAR_HDONE + 0), TC_EPI_WARPS + extra);
+    mbar_init(bar0 + 8 * (BAR_HDONE + 1), TC_EPI_WARPS + extra);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) tc_alloc(sbase + OFF_TMEM);
+  if (warp == W_ALLOC) { if (PAIR) tc_alloc2(sbase + OFF_TMEM); else tc_alloc(sbase + OFF_TMEM); }
   __syncthreads();     // frow visible to the epilogue's init below
 
-  // epilogue-side state (only meaningful for warps >= 4)
-  const int e = warp - TC_CTRL_WARPS;
+  // epilogue-side coordinates (meaningful for warps < 20)
   const int q = warp & 3;                    // TMEM lane quarter this warp may touch
-  const int sgrp = e >> 2;                   // column group 0..4 (4 units per chunk)
+  const int sgrp = warp >> 2;                // column group 0..4 (4 units per chunk)
   const int row = q * 32 + lane;             // window within the tile
   const uint32_t row_off = (uint32_t)((row >> 3) * 128 + (row & 7) * 16);
 
   // direction init: zero the hidden tiles, stage x(0), x(1) and the step-0 extras of h0[1]
   auto dir_init = [&](int dir) {
-    const int et = tid - TC_CTRL_WARPS * 32;
+    const int et = tid;
     uint4 z = make_uint4(0, 0, 0, 0);
     for (int i = et; i < (5 * TC_HTILE) / 16; i += TC_EPI_THREADS)
       *reinterpret_cast<uint4*>(smem + OFF_H0 + i * 16) = z;
@@ -196,95 +277,147 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
     fence_async_smem();
     epi_bar();
   };
-  if (warp >= TC_CTRL_WARPS) {
-    for (int i = tid - TC_CTRL_WARPS * 32; i < 5 * 128; i += TC_EPI_THREADS) s_part[i] = 0.f;
+  if (warp < TC_EPI_WARPS) {
+    for (int i = tid; i < 5 * 128; i += TC_EPI_THREADS) s_part[i] = 0.f;
     dir_init(0);
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();       // both CTAs' barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp == 0) {
-    // ================= weight producer =================
-    if (lane == 0) {
-      uint32_t st = 0;
-      int g = 0;
-      for (int dir = 0; dir < 2; ++dir)
-        for (int d = 0; d < 13; ++d)
-          for (int l = 0; l < 3; ++l) {
-            const int t = d - l;
-            if (t < 0 || t > 10) continue;
-            if (g++ >= max_steps) continue;
-            const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(w.wtc[dir][l]);
-            const int ncols = l == 0 ? 14 : 26;
-            for (int j = 0; j < TC_NCHUNK; ++j) {
-              for (int half = 0; half < (l == 0 ? 1 : 2); ++half) {
-                const uint32_t slot = st % TC_NSTAGE, use = st / TC_NSTAGE;
-                if (use > 0) mbar_wait(bar0 + 8 * (BAR_EMPTY + slot), (use - 1) & 1);
-                const uint32_t bytes = (half == 0 ? 14 : 12) * TC_BCOL;
-                mbar_expect_tx(bar0 + 8 * (BAR_FULL + slot), bytes);
-                bulk_g2s(sbase + OFF_W + slot * TC_STAGE, wsrc + (size_t)(j * ncols + half * 14) * TC_BCOL, bytes,
-                         bar0 + 8 * (BAR_FULL + slot));
-                ++st;
-              }
-            }
-          }
+// walks the 66 cell-steps in wavefront order; BODY sees dir, d, l, t, g
+#define FOR_EACH_STEP(...)                                    \
+  { int g = 0;                                                \
+    for (int dir = 0; dir < 2; ++dir)                         \
+      for (int d = 0; d < 13; ++d)                            \
+        _Pragma("unroll") for (int l = 0; l < 3; ++l) {       \
+          const int t = d - l;                                \
+          if (t < 0 || t > 10) continue;                      \
+          if (g < max_steps) { __VA_ARGS__ }                  \
+          ++g;                                                \
+        } }
+
+  if (warp == W_PROD) {
+    // ================= weight producer: one stage = one N-chunk of this CTA's gate columns =================
+    if (lane == 0 && !dbg_noload) {
+      uint32_t slot = 0, use = 0;
+      FOR_EACH_STEP({
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(PAIR ? w.wtc2[dir][l] : w.wtc[dir][l]);
+        const int ncols = l == 0 ? 14 : 26;
+        const uint32_t bytes = ncols * G::BCOL;
+        for (int j = 0; j < TC_NCHUNK; ++j) {
+          if (use > 0) mbar_wait(bar0 + 8 * (BAR_EMPTY + slot), (use - 1) & 1);
+          mbar_expect_tx(bar0 + 8 * (BAR_FULL + slot), bytes);
+          // image: [chunk j][cta r][K core column][n][8]
+          bulk_g2s(sbase + OFF_W + slot * G::STAGE, wsrc + (size_t)((j * G::NCTA + crank) * ncols) * G::BCOL, bytes,
+                   bar0 + 8 * (BAR_FULL + slot));
+          if (++slot == G::NSTAGE) { slot = 0; ++use; }
+        }
+      })
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
+  } else if (PAIR && !leader && warp >= W_MMA) {
+    // ================= peer-side relays: forward one arrival per phase to the leader =================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(128, TC_CHUNK_N);
-      uint32_t st = 0, tslot = 0, tuse = 0;
-      int g = 0;
-      for (int dir = 0; dir < 2; ++dir)
-        for (int d = 0; d < 13; ++d)
-          for (int l = 0; l < 3; ++l) {
-            const int t = d - l;
-            if (t < 0 || t > 10) continue;
-            if (g >= max_steps) { ++g; continue; }
-            // inputs of this cell-step were written by the epilogues of steps <= g-2, or g-1 in
-            // the fill/drain corners of the wavefront (and across the direction switch)
-            if (g >= 2) mbar_wait(bar0 + 8 * (BAR_HDONE + (g & 1)), ((g - 2) >> 1) & 1);
-            const bool wait1 = (d == 0 && dir > 0) || (d == 1 && l == 0) || d == 12;
-            if (wait1 && g >= 1) mbar_wait(bar0 + 8 * (BAR_HDONE + ((g - 1) & 1)), ((g - 1) >> 1) & 1);
+      if (warp == W_RELAY) {                    // "my half of the stage has landed"
+        if (!dbg_noload) {
+          uint32_t slot = 0, use = 0;
+          FOR_EACH_STEP({
+            for (int j = 0; j < TC_NCHUNK; ++j) {
+              mbar_wait(bar0 + 8 * (BAR_FULL + slot), use & 1);
+              mbar_arrive_remote(bar0 + 8 * (BAR_FULL + slot), 0);
+              if (++slot == G::NSTAGE) { slot = 0; ++use; }
+            }
+          })
+        }
+      } else if (warp == W_MMA) {               // "my epilogue has drained accumulator slot"
+        uint32_t tslot = 0, tuse = 0;
+        FOR_EACH_STEP({
+          for (int j = 0; j < TC_NCHUNK; ++j) {
+            mbar_wait(bar0 + 8 * (BAR_TEMPTY + tslot), tuse & 1);
+            mbar_arrive_remote(bar0 + 8 * (BAR_TEMPTY + tslot), 0);
+            if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
+          }
+        })
+      } else {                                  // "my epilogue has written the hidden state of step g"
+        FOR_EACH_STEP({
+          mbar_wait(bar0 + 8 * (BAR_HDONE + (g & 1)), (g >> 1) & 1);
+          mbar_arrive_remote(bar0 + 8 * (BAR_HDONE + (g & 1)), 0);
+        })
+      }
+    }
+  } else if ((warp == W_MMA || warp == W_RELAY) && leader) {
+    // ================= MMA issuers =================
+    // Issuing is single-threaded and latency-bound (two mbarrier waits + 13 tcgen05.mma + two commits per
+    // N-chunk), so TWO threads in different warps take alternate chunks; chunks own disjoint accumulator
+    // slots and weight stages, and each thread's commits cover exactly its own MMAs.
+    if (lane == 0) {
+      const uint32_t mine = warp == W_MMA ? 0u : 1u;
+      constexpr uint32_t idesc = umma_idesc(PAIR ? 256 : 128, TC_CHUNK_N);
+      constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);         // SBO = 128 B, descriptor version 1
+      constexpr uint32_t b_step = (2 * G::BCOL) >> 4;                // two K core columns per MMA
+      uint32_t slot = 0, use = 0, tslot = 0, tuse = 0, c = 0;
+      FOR_EACH_STEP({
+        if (mine == 0) TS(g * 8 + 0);
+        // inputs of this cell-step were written by the epilogues of steps <= g-2, or g-1 in the
+        // fill/drain corners of the wavefront (and across the direction switch)
+        if (g >= 2) mbar_wait_cluster(bar0 + 8 * (BAR_HDONE + (g & 1)), ((g - 2) >> 1) & 1);
+        const bool wait1 = (d == 0 && dir > 0) || (d == 1 && l == 0) || d == 12;
+        if (wait1 && g >= 1) mbar_wait_cluster(bar0 + 8 * (BAR_HDONE + ((g - 1) & 1)), ((g - 1) >> 1) & 1);
+        tc_fence_after();
+        if (mine == 0) TS(g * 8 + 1);
+        // A operand = ascending chain of core columns [n0 columns at base0 | rest at base1]; one
+        // descriptor (low word) per K=16 step, shared by the five N-chunks of the step
+        uint32_t base0, base1;
+        const int n0 = l == 0 ? 1 : TC_HCOLS;
+        const int nk16 = l == 0 ? 7 : 13;
+        if (l == 0)      { base0 = sbase + OFF_X + (t & 1) * TC_ACOL;   base1 = sbase + OFF_H0 + ((t + 1) & 1) * TC_HTILE; }
+        else if (l == 1) { base0 = sbase + OFF_H0 + (t & 1) * TC_HTILE; base1 = sbase + OFF_H1 + ((t + 1) & 1) * TC_HTILE; }
+        else             { base0 = sbase + OFF_H1 + (t & 1) * TC_HTILE; base1 = sbase + OFF_H2; }
+        uint32_t a_lo[13];
+        _Pragma("unroll")
+        for (int i = 0; i < 13; ++i) {
+          if (i >= nk16) break;
+          const int v0 = 2 * i, v1 = v0 + 1;
+          const uint32_t a0 = v0 < n0 ? base0 + v0 * TC_ACOL : base1 + (v0 - n0) * TC_ACOL;
+          const uint32_t a1 = v1 < n0 ? base0 + v1 * TC_ACOL : base1 + (v1 - n0) * TC_ACOL;
+          a_lo[i] = ((a0 >> 4) & 0x3FFFu) | (((a1 - a0) >> 4) << 16);
+        }
+        for (int j = 0; j < TC_NCHUNK; ++j, ++c) {
+          if ((c & 1u) == mine) {
+            if (tuse > 0) mbar_wait_cluster(bar0 + 8 * (BAR_TEMPTY + tslot), (tuse - 1) & 1);
+            if (!dbg_noload) mbar_wait_cluster(bar0 + 8 * (BAR_FULL + slot), use & 1);
             tc_fence_after();
-            uint32_t base0, base1;
-            int n0;
-            if (l == 0)      { base0 = sbase + OFF_X + (t & 1) * TC_ACOL;   n0 = 1;        base1 = sbase + OFF_H0 + ((t + 1) & 1) * TC_HTILE; }
-            else if (l == 1) { base0 = sbase + OFF_H0 + (t & 1) * TC_HTILE; n0 = TC_HCOLS; base1 = sbase + OFF_H1 + ((t + 1) & 1) * TC_HTILE; }
-            else             { base0 = sbase + OFF_H1 + (t & 1) * TC_HTILE; n0 = TC_HCOLS; base1 = sbase + OFF_H2; }
-            for (int j = 0; j < TC_NCHUNK; ++j) {
-              if (tuse > 0) { mbar_wait(bar0 + 8 * (BAR_TEMPTY + tslot), (tuse - 1) & 1); tc_fence_after(); }
-              const uint32_t d_tmem = tmem_base + tslot * TC_CHUNK_N;
-              int k16 = 0;
-              for (int half = 0; half < (l == 0 ? 1 : 2); ++half) {
-                const uint32_t slot = st % TC_NSTAGE, use = st / TC_NSTAGE;
-                mbar_wait(bar0 + 8 * (BAR_FULL + slot), use & 1);
-                tc_fence_after();
-                const uint32_t wb = sbase + OFF_W + slot * TC_STAGE;
-                const int nk = half == 0 ? 7 : 6;
-                for (int i = 0; i < nk; ++i, ++k16) {
-                  const int v0 = 2 * k16, v1 = v0 + 1;
-                  const uint32_t a0 = v0 < n0 ? base0 + v0 * TC_ACOL : base1 + (v0 - n0) * TC_ACOL;
-                  const uint32_t a1 = v1 < n0 ? base0 + v1 * TC_ACOL : base1 + (v1 - n0) * TC_ACOL;
-                  tc_mma(d_tmem, umma_desc(a0, a1 - a0, 128), umma_desc(wb + i * 2 * TC_BCOL, TC_BCOL, 128), idesc,
-                         k16 > 0 ? 1u : 0u);
-                }
-                tc_commit(bar0 + 8 * (BAR_EMPTY + slot));     // stage free once these MMAs retire
-                ++st;
+            const uint32_t d_tmem = tmem_base + tslot * TC_CHUNK_N;
+            const uint32_t b_lo = (((sbase + OFF_W + slot * G::STAGE) >> 4) & 0x3FFFu) | ((uint32_t)(G::BCOL >> 4) << 16);
+            if (!dbg_nomma) {
+              _Pragma("unroll")
+              for (int i = 0; i < 13; ++i) {
+                if (i >= nk16) break;
+                const uint64_t ad = ((uint64_t)desc_hi << 32) | a_lo[i];
+                const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + i * b_step);
+                if (PAIR) tc_mma2(d_tmem, ad, bd, idesc, i > 0 ? 1u : 0u);
+                else tc_mma(d_tmem, ad, bd, idesc, i > 0 ? 1u : 0u);
               }
-              tc_commit(bar0 + 8 * (BAR_TFULL + tslot));      // accumulator chunk ready
-              if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
             }
-            ++g;
+            // weight stage reusable / accumulator chunk ready once these MMAs retire (in both CTAs of a pair)
+            if (PAIR) { tc_commit2(bar0 + 8 * (BAR_EMPTY + slot)); tc_commit2(bar0 + 8 * (BAR_TFULL + tslot)); }
+            else      { tc_commit(bar0 + 8 * (BAR_EMPTY + slot));  tc_commit(bar0 + 8 * (BAR_TFULL + tslot)); }
+            if (mine == 0 || j == 1 || j == 3) TS(g * 8 + 2 + j);
           }
+          if (++slot == G::NSTAGE) { slot = 0; ++use; }
+          if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
+        }
+      })
     }
-  } else if (warp >= TC_CTRL_WARPS) {
+  } else if (warp < TC_EPI_WARPS) {
     // ================= epilogue: gates -> (c, h) =================
     __half2 cst[3][TC_NCHUNK][2];
     uint32_t tslot = 0, tuse = 0;
     int g = 0;
+    const bool stamp = lane == 0 && (warp == 0 || warp == TC_EPI_WARPS - 1);
+    const int ts0 = 1024 + (warp ? 2048 : 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sgrp * 16;
     for (int dir = 0; dir < 2; ++dir) {
 #pragma unroll
@@ -315,18 +448,22 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           uint32_t hkeep[TC_NCHUNK][2];
 #pragma unroll
           for (int j = 0; j < TC_NCHUNK; ++j) {
+            if (stamp) TS(ts0 + g * 16 + 3 * j);
             mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
             tc_fence_after();
+            if (stamp) TS(ts0 + g * 16 + 3 * j + 1);
             uint32_t v[16];
             tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
             tc_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_TEMPTY + tslot));
+            if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_TEMPTY + tslot));      // CTA-local; the peer's relay forwards
             if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
-            float hn[4];
+            if (stamp) TS(ts0 + g * 16 + 3 * j + 2);
+            float hn[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
+              if (dbg_nomath) break;
               const float2 cp = __half22float2(cst[l][j][p]);
               float cn[2];
 #pragma unroll
@@ -375,7 +512,8 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_HDONE + (g & 1)));
+          if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_HDONE + (g & 1)));         // CTA-local; the peer's relay forwards
+          if (stamp) TS(ts0 + g * 16 + 15);
           ++g;
         }
       }
@@ -390,12 +528,15 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
       if (pred_out) pred_out[win0 + row] = dl > 0.f ? 1 : 0;
     }
   }
+#undef FOR_EACH_STEP
+#undef TS
   tc_fence_before();
   __syncthreads();
   if (dbg != nullptr && blockIdx.x == 0)
     for (int i = tid; i < OFF_W / 16; i += TC_THREADS)
       reinterpret_cast<uint4*>(dbg)[i] = *reinterpret_cast<const uint4*>(smem + i * 16);
-  if (warp == 2) { tc_fence_after(); tc_dealloc(tmem_base); }
+  if (PAIR) cluster_sync_all();       // the peer may still be reading this CTA's operands / signalling its barriers
+  if (warp == W_ALLOC) { tc_fence_after(); if (PAIR) tc_dealloc2(tmem_base); else tc_dealloc(tmem_base); }
 }
 
 // ---- descriptor / TMEM / bulk-copy self-test: D[128,n] = A[128,k] * B[n,k]^T -----------------
@@ -476,7 +617,9 @@ float h_bf16f(uint16_t b) {
 //            cols 13..25 = own hidden tile (extras unused).
 // The sigmoid gates (i, f, o) are pre-scaled by 0.5 because the epilogue evaluates
 // sigmoid(x) = 0.5*tanh(x/2)+0.5; forget_bias = 1.0 (BasicLSTMCell) is folded into the bias.
-void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, std::vector<uint16_t>& img) {
+// pair = true: [chunk j][cta r][core column kc][n 40][8 k], CTA r owning gate columns n = 40 r .. 40 r + 39
+// of the chunk (tcgen05.mma.cta_group::2 takes the first half of B's N rows from the even CTA).
+void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool pair, std::vector<uint16_t>& img) {
   const int ncols = layer == 0 ? 14 : 26;
   img.assign((size_t)TC_NCHUNK * ncols * TC_CHUNK_N * 8, 0);
   for (int j = 0; j < TC_NCHUNK; ++j)
@@ -512,17 +655,44 @@ void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, std::
               if (kk < DM_HIDDEN) val = wref(DM_HIDDEN + kk);
             }
           }
-          img[(((size_t)j * ncols + kc) * TC_CHUNK_N + n) * 8 + e] = val;
+          if (pair) img[((((size_t)j * 2 + n / 40) * ncols + kc) * 40 + n % 40) * 8 + e] = val;
+          else img[(((size_t)j * ncols + kc) * TC_CHUNK_N + n) * 8 + e] = val;
         }
       }
 }
 
 static int tc_prepare(dm_ctx* ctx) {
   if (!ctx->tc_attr_set) {
-    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     DM_CUDA(ctx, cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ctx->tc_attr_set = true;
   }
+  return DM_OK;
+}
+
+static int tc_launch(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_pad, float* p1,
+                     uint8_t* pred, int max_steps, unsigned char* dbg) {
+  const unsigned tiles = (unsigned)(n_pad / DM_TILE_M);       // n_pad is a multiple of 256: an even number of tiles
+  if (ctx->tc_pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = TC_SMEM;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstm_tc<true>, feat_tc, win_frow, ctx->w, p1, pred, max_steps, dbg));
+  } else {
+    k_lstm_tc<false><<<tiles, TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred, max_steps, dbg);
+  }
+  ctx->launches += 1;
+  DM_CUDA(ctx, cudaGetLastError());
   return DM_OK;
 }
 
@@ -532,15 +702,11 @@ int dm_launch_lstm_tc(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* 
   if (n_pad == 0) return DM_OK;
   int rc = tc_prepare(ctx);
   if (rc != DM_OK) return rc;
-  k_lstm_tc<<<(unsigned)(n_pad / DM_TILE_M), TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred,
-                                                                                 2 * TC_STEPS_PER_DIR, nullptr);
-  ctx->launches += 1;
-  DM_CUDA(ctx, cudaGetLastError());
-  return DM_OK;
+  return tc_launch(ctx, feat_tc, win_frow, n_pad, p1, pred, 2 * TC_STEPS_PER_DIR, nullptr);
 }
 
-// debug: run the first `max_steps` cell-steps of tile 0 and return its shared-memory operand
-// region (x columns + the five hidden tiles, OFF_W bytes)
+// debug: run the first `max_steps` cell-steps and return tile 0's shared-memory operand region
+// (x columns + the five hidden tiles, OFF_W bytes)
 int dm_tc_debug(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_windows, float* p1,
                 uint8_t* pred, int max_steps, unsigned char* dump_host, int64_t dump_cap) {
   const int64_t n_pad = dm_pad_windows(n_windows);
@@ -548,15 +714,17 @@ int dm_tc_debug(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_fr
   int rc = tc_prepare(ctx);
   if (rc != DM_OK) return rc;
   unsigned char* dbg = nullptr;
-  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dbg), OFF_W));
-  k_lstm_tc<<<(unsigned)(n_pad / DM_TILE_M), TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred,
-                                                                                 max_steps, dbg);
-  ctx->launches += 1;
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&dbg), OFF_W + TS_BYTES));
+  cudaMemsetAsync(dbg, 0, OFF_W + TS_BYTES, ctx->stream);
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  rc = tc_launch(ctx, feat_tc, win_frow, n_pad, p1, pred, max_steps, dbg);
+  cudaEventRecord(ctx->ev2, ctx->stream);
+  cudaError_t e = rc == DM_OK ? cudaStreamSynchronize(ctx->stream) : cudaErrorUnknown;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ctx->lstm_ms, ctx->ev1, ctx->ev2);
   if (e == cudaSuccess && dump_host)
-    e = cudaMemcpy(dump_host, dbg, (size_t)std::min<int64_t>(dump_cap, OFF_W), cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(dump_host, dbg, (size_t)std::min<int64_t>(dump_cap, OFF_W + TS_BYTES), cudaMemcpyDeviceToHost);
   cudaFree(dbg);
+  if (rc != DM_OK) return rc;
   if (e != cudaSuccess) { dm_set_error(ctx, std::string("dm_tc_debug: ") + cudaGetErrorString(e)); return DM_ERR_CUDA; }
   return DM_OK;
 }

@@ -50,7 +50,8 @@ enum dm_status {
 /* arithmetic of the BiLSTM */
 enum dm_precision {
   DM_FP32 = 0,   /* fp32 FMA + accurate expf/tanhf: the parity path (<=1e-4 on p1) */
-  DM_BF16 = 1    /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM */
+  DM_BF16 = 1,   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM; CTA pairs (cta_group::2) */
+  DM_BF16_1CTA = 2  /* same arithmetic, one CTA per 128-window tile (cta_group::1); kept for A/B measurements */
 };
 
 /* per-read status written by dm_detect_batch (mirrors sp_param['f5status']) */
