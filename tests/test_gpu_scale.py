@@ -1,0 +1,67 @@
+"""Size-independent properties at a BASELINE-sized batch (no oracle run needed): coverage equals the
+alignment-derived count, two precisions agree up to the bf16 flip rate, accumulation is linear."""
+import numpy as np
+import pytest
+
+from conftest import golden_model
+
+pytestmark = pytest.mark.gpu
+
+
+def test_full_size_batch_properties():
+    from deepmod_b200 import capi, checkpoint, synth
+    genome = synth.make_genome([600000, 400000], seed=41)
+    batch = synth.make_reads(genome, 120, seed=42, align_seed=43, mean_len=8000, len_lo=600, len_hi=60000, p_bad_read=0.05)
+    pb = capi.PackedBatch(batch)
+    assert pb.n_windows > 500000
+    model = checkpoint.Model.from_dict(golden_model("conmodC_P100"))
+    res = {}
+    for prec in (capi.FP32, capi.BF16, capi.BF16_1CTA):
+        with capi.Context(model, 0, prec) as ctx:
+            ctx.set_genome([600000, 400000], "C")
+            p1, pred, status = ctx.detect_batch(pb)
+            hist = {(ci, s): ctx.hist_nonzero(ci, s) for ci in range(2) for s in "+-"}
+            ctx.detect_batch(pb)
+            hist2 = {(ci, s): ctx.hist_nonzero(ci, s) for ci in range(2) for s in "+-"}
+        res[prec] = (p1, pred, status, hist)
+        for k in hist:                                   # linearity of the accumulator
+            assert np.array_equal(hist[k][0], hist2[k][0]) and np.array_equal(2 * hist[k][1], hist2[k][1])
+            assert np.array_equal(2 * hist[k][2], hist2[k][2])
+    p1, pred, status, hist = res[capi.FP32]
+    assert set(np.unique(status)) <= {0, 1} and (status == 1).sum() >= 1
+    ok_reads = np.flatnonzero(status == 0)
+    # coverage/touched rows from the alignment alone (independent of the model)
+    want_cov = {}
+    for r in ok_reads:
+        c0, c1 = int(batch["col_off"][r]), int(batch["col_off"][r + 1])
+        refb, readb, pos = batch["col_refbase"][c0:c1], batch["col_readbase"][c0:c1], batch["col_refpos"][c0:c1]
+        sel = refb == ord("C")
+        key = (int(batch["contig"][r]), "+" if batch["strand"][r] > 0 else "-")
+        d = want_cov.setdefault(key, {})
+        for p, gap in zip(pos[sel], readb[sel] == ord("-")):
+            d[int(p)] = d.get(int(p), 0) + (0 if gap else 1)
+    for key, d in want_cov.items():
+        pos, cov, mod = hist[key]
+        assert list(pos) == sorted(d)
+        assert [d[int(p)] for p in pos] == list(cov)
+        assert np.all(mod <= cov)
+    # sum of mod counts == number of predicted-modified C columns
+    total_mod = sum(int(h[2].sum()) for h in hist.values())
+    ok_w = np.repeat(status == 0, pb.n_windows_per_read)
+    k = 0
+    want_mod = 0
+    w_off = np.concatenate([[0], np.cumsum(pb.n_windows_per_read)])
+    for r in ok_reads:
+        c0, c1 = int(batch["col_off"][r]), int(batch["col_off"][r + 1])
+        refb, readb = batch["col_refbase"][c0:c1], batch["col_readbase"][c0:c1]
+        nongap = readb != ord("-")
+        pr = pred[w_off[r]:w_off[r + 1]]
+        want_mod += int(pr[(refb[nongap] == ord("C"))].sum())
+    assert total_mod == want_mod
+    # the two tensor-core variants are the same arithmetic: bit-identical results
+    assert np.array_equal(res[capi.BF16][0], res[capi.BF16_1CTA][0])
+    # bf16 vs fp32
+    flips = float(np.mean(res[capi.BF16][1][ok_w] != pred[ok_w]))
+    err = np.abs(res[capi.BF16][0][ok_w] - p1[ok_w])
+    print("full-size: %d windows, bf16 flip rate %.5f, mean |dp1| %.2e, max %.3f" % (ok_w.sum(), flips, err.mean(), err.max()))
+    assert flips < 0.003 and err.mean() < 2e-3
