@@ -278,7 +278,9 @@ def main():
     if os.path.isfile(tpath):
         try:
             with open(tpath) as fh:
-                traffic = json.load(fh).get(args.precision)
+                rec = json.load(fh).get(args.precision)
+            # measured once under ncu (bytes per mapped base of the same kernel), scaled to this launch
+            traffic = rec["dram_bytes_per_base"] * n_ok if rec else None
         except Exception:
             traffic = None
     if args.precision == "bf16":

@@ -471,10 +471,14 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
                 const int u = 2 * p + k;
                 const float ti = tanh_mufu(__uint_as_float(v[4 * u + 0]));
                 const float tj = tanh_mufu(__uint_as_float(v[4 * u + 1]));
-                const float tf = tanh_mufu(__uint_as_float(v[4 * u + 2]));
                 const float to = tanh_mufu(__uint_as_float(v[4 * u + 3]));
-                const float si = fmaf(ti, 0.5f, 0.5f), sf = fmaf(tf, 0.5f, 0.5f), so = fmaf(to, 0.5f, 0.5f);
-                cn[k] = fmaf(k == 0 ? cp.x : cp.y, sf, si * tj);
+                const float si = fmaf(ti, 0.5f, 0.5f), so = fmaf(to, 0.5f, 0.5f);
+                if (t == 0) {                         // c_prev == 0: the forget gate cannot matter
+                  cn[k] = si * tj;
+                } else {
+                  const float sf = fmaf(tanh_mufu(__uint_as_float(v[4 * u + 2])), 0.5f, 0.5f);
+                  cn[k] = fmaf(k == 0 ? cp.x : cp.y, sf, si * tj);
+                }
                 hn[u] = tanh_mufu(cn[k]) * so;
               }
               cst[l][j][p] = __floats2half2_rn(cn[0], cn[1]);

@@ -180,3 +180,88 @@ def test_detect_batch_bf16_close(capi, golden_batch, tmp_path):
         rows = [ln.split(" ") for ln in text.splitlines()]
         pos, cov, mod = hist[(names.index(key[:-1]), key[-1])]
         assert [int(r[1]) for r in rows] == list(pos) and [int(r[9]) for r in rows] == list(cov)
+
+
+def test_session_seam_drives_the_reference_batch_loop(capi, golden_batch):
+    """b1 seam: the reference's mPredict1 batch loop (restated in oracle.detect_ref.predict_read,
+    myDetect.py:805-820) running against B200Session instead of a TF session."""
+    from deepmod_b200 import checkpoint
+    from deepmod_b200.session import B200Session
+    from oracle import detect_ref
+    batch, names, lens = golden_batch
+    g = golden_reads("conmodC_P100")
+    sess = B200Session(checkpoint.Model.from_dict(golden_model("conmodC_P100")))
+    preds = []
+    for r in range(len(batch["start_clip"])):
+        rd = detect_ref.unpack_read(batch, r)
+        L = len(rd["ev_mean"])
+        if L - rd["start_clip"] - rd["end_clip"] < 50:
+            continue
+        mf, st = detect_ref.get_feature(rd["ev_mean"], rd["ev_stdv"], rd["ev_len"], rd["ev_base"], rd["refbase"],
+                                        rd["readbase"], rd["start_clip"], rd["end_clip"])
+        if st != detect_ref.STATUS_OK:
+            continue
+        win = detect_ref.windows_from_features(mf, L, rd["start_clip"], rd["end_clip"])
+        calls = sess.calls
+        preds.append(detect_ref.predict_read(sess, win))
+        assert sess.calls - calls == len(detect_ref.split_groups(len(win)))     # batch policy :808-812
+    sess.close()
+    assert np.array_equal(np.concatenate(preds).astype(np.uint8), g["pred"])
+
+
+def test_mixed_read_lengths_6mA_model(capi):
+    """BASELINE configs[3]: rnn_conmodA_E1m2 (--Base A), log-uniform read lengths incl. one > 100 kb and
+    reads below the 50-event floor; fp32 path against the CPU restatement (torch fp32 session)."""
+    from deepmod_b200 import synth
+    from oracle import bilstm, detect_ref
+    genome = synth.make_genome([400000], seed=51)
+    parts = [synth.make_reads(genome, 14, seed=52, align_seed=53, length_kind="loguniform", len_lo=40, len_hi=30000, max_clip=12),
+             synth.make_reads(genome, 1, seed=54, align_seed=55, length_kind="fixed", mean_len=110000, len_lo=40, len_hi=200000)]
+    batch = synth.concat_batches(parts)
+    m = golden_model("conmodA_E1m2")
+    sess = bilstm.TorchSession(m, threads=8)
+    acc, status = detect_ref.detect_batch(sess, batch, ["c"], "A")
+    want = detect_ref.bed_by_contig_strand(acc)
+    with make_ctx(capi, "conmodA_E1m2") as ctx:
+        ctx.set_genome([400000], "A")
+        p1, pred, st = ctx.detect_batch(batch)
+        got = {}
+        for s in "+-":
+            pos, cov, mod = ctx.hist_nonzero(0, s)
+            got[s] = (pos, cov, mod)
+    assert list(st) == status and 3 in status and 0 in status
+    for s in "+-":
+        lines = [ln.split(" ") for ln in want.get(("c", s), "").splitlines()]
+        pos, cov, mod = got[s]
+        assert [int(x[1]) for x in lines] == list(pos) and [int(x[9]) for x in lines] == list(cov)
+        # two independent fp32 implementations: allow argmax flips only where p1 is within 1e-4 of 0.5
+        dm = np.abs(np.array([int(x[11]) for x in lines]) - mod)
+        assert dm.sum() <= 2, dm.sum()
+
+
+def test_hg38_scale_accumulator(capi):
+    """BASELINE configs[4] layout: the dense per-position accumulator for the 25 hg38 contigs (2 x 3.1 G
+    cells = 50 GB) lives in HBM; reads landing on several contigs reduce into the right blocks."""
+    import torch
+    from deepmod_b200 import synth
+    if torch.cuda.mem_get_info()[0] < 70e9:
+        pytest.skip("needs > 70 GB of free HBM")
+    lens = synth.HG38_LEN
+    genome = synth.make_genome([200000], seed=61)
+    base = synth.make_reads(genome, 6, seed=62, align_seed=63, mean_len=1500, len_lo=300, len_hi=4000)
+    with make_ctx(capi, "conmodC_P100") as ctx:
+        ctx.set_genome(lens, "C")
+        ptr, n_cells = ctx.hist_device_ptr()
+        assert n_cells == 2 * sum(lens)
+        ctx.detect_batch(base)                                   # everything on contig 0 (chr1)
+        ref = {s: ctx.hist_nonzero(0, s) for s in "+-"}
+        for ci in (7, 22, 24):                                   # chr8, chrX, chrM-sized blocks
+            if lens[ci] < 200000:
+                continue
+            moved = dict(base)
+            moved["contig"] = np.full_like(base["contig"], ci)
+            ctx.detect_batch(moved)
+            for s in "+-":
+                a, b = ctx.hist_nonzero(ci, s), ref[s]
+                assert all(np.array_equal(x, y) for x, y in zip(a, b))
+        assert len(ctx.hist_nonzero(1, "+")[0]) == 0
