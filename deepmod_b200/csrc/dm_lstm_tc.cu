@@ -210,7 +210,8 @@ __device__ __forceinline__ int tau_row(int dir, int tau) { return dir == 0 ? tau
 template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__ win_frow, dm_dev_weights w,
-          float* __restrict__ p1_out, uint8_t* __restrict__ pred_out, int max_steps, unsigned char* __restrict__ dbg) {
+          float* __restrict__ p1_out, uint8_t* __restrict__ pred_out, int n_tiles, int max_steps,
+          unsigned char* __restrict__ dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + OFF_BAR;
@@ -225,14 +226,16 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = PAIR ? cluster_rank() : 0u;      // 0 = leader (issues the MMAs of the pair)
   const bool leader = crank == 0;
-  const int64_t win0 = (int64_t)blockIdx.x * DM_TILE_M;
+  // persistent: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (a pair walks tile pairs);
+  // barriers, TMEM and the weight ring live across tiles, only the hidden state is re-initialised
+  const int n_iter = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   int* s_frow = reinterpret_cast<int*>(smem + OFF_FROW);
   float* s_part = reinterpret_cast<float*>(smem + OFF_PART);
   float* s_cls = reinterpret_cast<float*>(smem + OFF_CLS);
   volatile uint32_t* s_tmem = reinterpret_cast<volatile uint32_t*>(smem + OFF_TMEM);
 
   // ---- one-time setup ----
-  if (tid < DM_TILE_M) s_frow[tid] = win_frow[win0 + tid];
+  if (tid < DM_TILE_M) s_frow[tid] = win_frow[(int64_t)blockIdx.x * DM_TILE_M + tid];
   if (tid < 200) s_cls[tid] = w.cls_d[tid];
   if (tid == 0) {
     // leader barriers also collect one forwarded arrival per phase from the peer CTA
@@ -289,7 +292,10 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
 
 // walks the 66 cell-steps in wavefront order; BODY sees dir, d, l, t, g
 #define FOR_EACH_STEP(...)                                    \
-  { int g = 0;                                                \
+  for (int it = 0; it < n_iter; ++it) {                       \
+    int g = 0;                                                \
+    const int G0 = it * 2 * TC_STEPS_PER_DIR;                 \
+    (void)G0;                                                 \
     for (int dir = 0; dir < 2; ++dir)                         \
       for (int d = 0; d < 13; ++d)                            \
         _Pragma("unroll") for (int l = 0; l < 3; ++l) {       \
@@ -342,8 +348,9 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
         })
       } else {                                  // "my epilogue has written the hidden state of step g"
         FOR_EACH_STEP({
-          mbar_wait(bar0 + 8 * (BAR_HDONE + (g & 1)), (g >> 1) & 1);
-          mbar_arrive_remote(bar0 + 8 * (BAR_HDONE + (g & 1)), 0);
+          const int G = G0 + g;
+          mbar_wait(bar0 + 8 * (BAR_HDONE + (G & 1)), (G >> 1) & 1);
+          mbar_arrive_remote(bar0 + 8 * (BAR_HDONE + (G & 1)), 0);
         })
       }
     }
@@ -362,9 +369,10 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
         if (mine == 0) TS(g * 8 + 0);
         // inputs of this cell-step were written by the epilogues of steps <= g-2, or g-1 in the
         // fill/drain corners of the wavefront (and across the direction switch)
-        if (g >= 2) mbar_wait_cluster(bar0 + 8 * (BAR_HDONE + (g & 1)), ((g - 2) >> 1) & 1);
-        const bool wait1 = (d == 0 && dir > 0) || (d == 1 && l == 0) || d == 12;
-        if (wait1 && g >= 1) mbar_wait_cluster(bar0 + 8 * (BAR_HDONE + ((g - 1) & 1)), ((g - 1) >> 1) & 1);
+        const int G = G0 + g;
+        if (G >= 2) mbar_wait_cluster(bar0 + 8 * (BAR_HDONE + (G & 1)), ((G - 2) >> 1) & 1);
+        const bool wait1 = d == 0 || (d == 1 && l == 0) || d == 12;     // d == 0: first step after a (re-)initialisation
+        if (wait1 && G >= 1) mbar_wait_cluster(bar0 + 8 * (BAR_HDONE + ((G - 1) & 1)), ((G - 1) >> 1) & 1);
         tc_fence_after();
         if (mine == 0) TS(g * 8 + 1);
         // A operand = ascending chain of core columns [n0 columns at base0 | rest at base1]; one
@@ -415,10 +423,13 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
     // ================= epilogue: gates -> (c, h) =================
     __half2 cst[3][TC_NCHUNK][2];
     uint32_t tslot = 0, tuse = 0;
-    int g = 0;
-    const bool stamp = lane == 0 && (warp == 0 || warp == TC_EPI_WARPS - 1);
     const int ts0 = 1024 + (warp ? 2048 : 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sgrp * 16;
+    for (int it = 0; it < n_iter; ++it) {
+    const int64_t win0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * DM_TILE_M;
+    const int G0 = it * 2 * TC_STEPS_PER_DIR;
+    const bool stamp = it == 0 && lane == 0 && (warp == 0 || warp == TC_EPI_WARPS - 1);
+    int g = 0;
     for (int dir = 0; dir < 2; ++dir) {
 #pragma unroll
       for (int l = 0; l < 3; ++l)
@@ -510,9 +521,29 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           if (l == 0 && sgrp == 0 && t + 2 <= 10)
             *reinterpret_cast<uint4*>(smem + OFF_X + (t & 1) * TC_ACOL + row_off) = xnext;
           if (l == 2 && t == 10) s_part[sgrp * 128 + row] += cls_acc;
-          if (dir == 0 && d == 12 && max_steps > TC_STEPS_PER_DIR) {
-            epi_bar();          // every warp is done with direction 0
-            dir_init(1);
+          if (d == 12) {
+            // last cell-step of a direction: everything the next direction / next tile needs is staged
+            // BEFORE this step is reported done, because the issuers' next step waits on exactly that
+            epi_bar();          // every warp is done with this direction
+            if (dir == 0) {
+              if (max_steps > TC_STEPS_PER_DIR) dir_init(1);
+            } else {
+              if (sgrp == 0) {
+                float dl = w.cls_db;
+#pragma unroll
+                for (int s = 0; s < 5; ++s) dl += s_part[s * 128 + row];
+                // softmax over two classes: p1 = 1/(1+exp(l0-l1)); argmax picks class 1 iff l1 > l0
+                if (p1_out) p1_out[win0 + row] = 1.0f / (1.0f + __expf(-dl));
+                if (pred_out) pred_out[win0 + row] = dl > 0.f ? 1 : 0;
+              }
+              if (it + 1 < n_iter) {
+                epi_bar();        // partial logits consumed
+                for (int i = tid; i < 5 * 128; i += TC_EPI_THREADS) s_part[i] = 0.f;
+                if (tid < DM_TILE_M) s_frow[tid] = win_frow[win0 + (int64_t)gridDim.x * DM_TILE_M + tid];
+                epi_bar();        // next tile's feature rows visible
+                dir_init(0);
+              }
+            }
           }
           fence_async_smem();
           __syncwarp();
@@ -522,14 +553,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
         }
       }
     }
-    epi_bar();
-    if (sgrp == 0) {
-      float dl = w.cls_db;
-#pragma unroll
-      for (int s = 0; s < 5; ++s) dl += s_part[s * 128 + row];
-      // softmax over two classes: p1 = 1/(1+exp(l0-l1)); argmax picks class 1 iff l1 > l0
-      if (p1_out) p1_out[win0 + row] = 1.0f / (1.0f + __expf(-dl));
-      if (pred_out) pred_out[win0 + row] = dl > 0.f ? 1 : 0;
+    (void)G0;
     }
   }
 #undef FOR_EACH_STEP
@@ -678,9 +702,12 @@ static int tc_prepare(dm_ctx* ctx) {
 static int tc_launch(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_pad, float* p1,
                      uint8_t* pred, int max_steps, unsigned char* dbg) {
   const unsigned tiles = (unsigned)(n_pad / DM_TILE_M);       // n_pad is a multiple of 256: an even number of tiles
+  // persistent CTAs: one per SM (an even number, so that pairs stay whole); the debug entry runs one tile per CTA
+  unsigned grid = (unsigned)(ctx->sm_count & ~1);
+  if (dbg != nullptr || max_steps != 2 * TC_STEPS_PER_DIR || grid > tiles) grid = tiles;
   if (ctx->tc_pair) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(tiles);
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.dynamicSmemBytes = TC_SMEM;
     cfg.stream = ctx->stream;
@@ -691,9 +718,9 @@ static int tc_launch(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* w
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstm_tc<true>, feat_tc, win_frow, ctx->w, p1, pred, max_steps, dbg));
+    DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstm_tc<true>, feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg));
   } else {
-    k_lstm_tc<false><<<tiles, TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred, max_steps, dbg);
+    k_lstm_tc<false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg);
   }
   ctx->launches += 1;
   DM_CUDA(ctx, cudaGetLastError());
