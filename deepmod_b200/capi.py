@@ -37,6 +37,10 @@ class DmBatch(C.Structure):
                 ("start_clip", _i32p), ("end_clip", _i32p), ("contig", _i32p), ("strand", _i8p)]
 
 
+class DmClusterWeights(C.Structure):
+    _fields_ = [("w1", _fp), ("b1", _fp), ("w2", _fp), ("b2", _fp), ("wo", _fp), ("bo", _fp)]
+
+
 class DeepModError(RuntimeError):
     pass
 
@@ -56,6 +60,13 @@ SIGNATURES = {
     "dm_hist_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _i64p]),
     "dm_hist_nonzero": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _i64p, _i32p, _i32p, _i64p]),
     "dm_write_bed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_char_p, C.c_char_p, _i64p]),
+    "dm_hist_load": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _i64p, _i32p, _i32p]),
+    "dm_write_merged_bed": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p, _i64p]),
+    "dm_cluster_set_sites": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, _i64p, _i8p]),
+    "dm_cluster_predict": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DmClusterWeights), C.c_int, C.c_int64, _i64p, _i8p,
+                                     _i32p, _i32p, _fp, _fp, _i32p, _i64p]),
+    "dm_write_cluster_bed": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DmClusterWeights), C.c_int, C.c_char_p, C.c_char_p,
+                                       _i64p]),
     "dm_detect_batch": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _fp, _u8p, _i32p]),
     "dm_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _i64p]),
     "dm_detect_resident": (C.c_int, [C.c_void_p, C.c_int]),
@@ -261,6 +272,55 @@ class Context(object):
         n = C.c_int64()
         s = 1 if strand in (1, "+") else -1
         self._check(self.lib.dm_write_bed(self._h, contig, s, chrom.encode(), path.encode(), C.byref(n)), "dm_write_bed")
+        return n.value
+
+    def hist_load(self, contig, strand, pos, cov, mod):
+        pos, cov, mod = _arr(pos, np.int64), _arr(cov, np.int32), _arr(mod, np.int32)
+        s = 1 if strand in (1, "+") else -1
+        self._check(self.lib.dm_hist_load(self._h, contig, s, len(pos), _ptr(pos, C.c_int64), _ptr(cov, C.c_int32),
+                                          _ptr(mod, C.c_int32)), "dm_hist_load")
+
+    def write_merged_bed(self, contig, chrom, path):
+        n = C.c_int64()
+        self._check(self.lib.dm_write_merged_bed(self._h, contig, chrom.encode(), path.encode(), C.byref(n)), "dm_write_merged_bed")
+        return n.value
+
+    # -- CpG-cluster second pass ---------------------------------------------------------------
+    @staticmethod
+    def _cluster_struct(weights):
+        keep = [_arr(weights[k], np.float32) for k in ("W_1", "b_1", "W_2", "b_2", "W_O", "b_O")]
+        if [a.size for a in keep] != [1400, 100, 2000, 20, 20, 1]:
+            raise ValueError("cluster model must be W_1[14,100] b_1[100] W_2[100,20] b_2[20] W_O[20,1] b_O[1]")
+        w = DmClusterWeights(*[_ptr(a, C.c_float) for a in keep])
+        return w, keep
+
+    def cluster_set_sites(self, contig, pos, strand):
+        pos, strand = _arr(pos, np.int64), _arr(strand, np.int8)
+        self._check(self.lib.dm_cluster_set_sites(self._h, contig, len(pos), _ptr(pos, C.c_int64), _ptr(strand, C.c_int8)),
+                    "dm_cluster_set_sites")
+
+    def cluster_predict(self, contig, weights, drop_unmodified=True, want_features=False):
+        w, keep = self._cluster_struct(weights)
+        n = C.c_int64()
+        self._check(self.lib.dm_cluster_predict(self._h, contig, C.byref(w), int(drop_unmodified), 0, None, None, None, None,
+                                                None, None, None, C.byref(n)), "dm_cluster_predict")
+        k = n.value
+        out = dict(pos=np.zeros(k, np.int64), strand=np.zeros(k, np.int8), cov=np.zeros(k, np.int32), mod=np.zeros(k, np.int32),
+                   prob=np.zeros(k, np.float32), pct=np.zeros(k, np.int32),
+                   features=np.zeros((k, 14), np.float32) if want_features else None)
+        if k:
+            self._check(self.lib.dm_cluster_predict(self._h, contig, C.byref(w), int(drop_unmodified), k, _ptr(out["pos"], C.c_int64),
+                                                    _ptr(out["strand"], C.c_int8), _ptr(out["cov"], C.c_int32),
+                                                    _ptr(out["mod"], C.c_int32), _ptr(out["features"], C.c_float),
+                                                    _ptr(out["prob"], C.c_float), _ptr(out["pct"], C.c_int32), C.byref(n)),
+                        "dm_cluster_predict")
+        return out
+
+    def write_cluster_bed(self, contig, weights, chrom, path, drop_unmodified=True):
+        w, keep = self._cluster_struct(weights)
+        n = C.c_int64()
+        self._check(self.lib.dm_write_cluster_bed(self._h, contig, C.byref(w), int(drop_unmodified), chrom.encode(), path.encode(),
+                                                  C.byref(n)), "dm_write_cluster_bed")
         return n.value
 
     # -- the hot path ------------------------------------------------------------------------

@@ -173,7 +173,7 @@ void dm_destroy(dm_ctx* ctx) {
     cudaFree(b->status); cudaFree(b->feat); cudaFree(b->feat_tc); cudaFree(b->p1); cudaFree(b->pred);
   }
   cudaFree(ctx->fw_x);
-  cudaFree(ctx->contig_off_d); cudaFree(ctx->cells);
+  cudaFree(ctx->contig_off_d); cudaFree(ctx->cells); cudaFree(ctx->motif);
   cudaFree(ctx->scratch); cudaFree(ctx->hbuf); cudaFree(ctx->dpart);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -419,6 +419,7 @@ int dm_set_genome(dm_ctx* ctx, int32_t n_contigs, const int64_t* contig_len, cha
     off[i + 1] = off[i] + contig_len[i];
   }
   cudaFree(ctx->cells); ctx->cells = nullptr;
+  cudaFree(ctx->motif); ctx->motif = nullptr;
   cudaFree(ctx->contig_off_d); ctx->contig_off_d = nullptr;
   ctx->n_cells = 2 * off[n_contigs];
   DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->cells), sizeof(unsigned long long) * (size_t)std::max<int64_t>(ctx->n_cells, 1)));
@@ -505,6 +506,93 @@ int dm_debug_tc_windows(dm_ctx* ctx, int64_t n, const float* X, int max_steps, u
   DM_TRY(dm_launch_windows_to_rows(ctx, ctx->fw_x, n, f.feat, f.feat_tc, f.win_frow));
   DM_TRY(dm_tc_debug(ctx, f.feat_tc, f.win_frow, n, f.p1, f.pred, max_steps, dump, dump_cap));
   if (p1_out) DM_CUDA(ctx, cudaMemcpy(p1_out, f.p1, sizeof(float) * n, cudaMemcpyDeviceToHost));
+  return DM_OK;
+}
+
+// ---- merged summary + cluster second pass ------------------------------------------------
+
+int dm_hist_load(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t n, const int64_t* pos, const int32_t* cov,
+                 const int32_t* mod) {
+  if (!ctx || (n > 0 && (!pos || !cov || !mod))) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  return dm_hist_load_rows(ctx, contig, strand, n, pos, cov, mod);
+}
+
+static void merged_line(FILE* fh, const char* chrom, long long pos, char base, char strand, long long cov, long long mod) {
+  // sum_chr_mod.py:63 (two spaces after the strand; percentage = int(mod*100/cov))
+  fprintf(fh, "%s %lld %lld %c %lld %c  %lld %lld 0,0,0 %lld %lld %lld", chrom, pos, pos + 1, base, cov < 1000 ? cov : 1000LL,
+          strand, pos, pos + 1, cov, cov > 0 ? (mod * 100) / cov : 0LL, mod);
+}
+
+int dm_write_merged_bed(dm_ctx* ctx, int32_t contig, const char* chrom, const char* path, int64_t* n_rows) {
+  if (!ctx || !chrom || !path) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<int64_t> pp, pm; std::vector<int32_t> cp, mp, cm, mm;
+  DM_TRY(dm_hist_compact(ctx, contig, 1, pp, cp, mp));
+  DM_TRY(dm_hist_compact(ctx, contig, -1, pm, cm, mm));
+  int64_t rows = 0;
+  FILE* fh = nullptr;
+  size_t i = 0, j = 0;
+  while (i < pp.size() || j < pm.size()) {       // keys sorted by (pos, strand), '+' < '-'
+    const bool plus = j >= pm.size() || (i < pp.size() && pp[i] <= pm[j]);
+    const long long pos = plus ? pp[i] : pm[j], cov = plus ? cp[i] : cm[j], mod = plus ? mp[i] : mm[j];
+    if (plus) ++i; else ++j;
+    if (mod == 0) continue;                      // sum_chr_mod.py:55-57
+    if (!fh) {
+      fh = fopen(path, "w");
+      if (!fh) return fail(ctx, DM_ERR_IO, std::string("dm_write_merged_bed: cannot open ") + path);
+    }
+    merged_line(fh, chrom, pos, ctx->base, plus ? '+' : '-', cov, mod);
+    fputc('\n', fh);
+    ++rows;
+  }
+  if (fh && fclose(fh) != 0) return fail(ctx, DM_ERR_IO, std::string("dm_write_merged_bed: write failed for ") + path);
+  if (n_rows) *n_rows = rows;
+  return DM_OK;
+}
+
+int dm_cluster_set_sites(dm_ctx* ctx, int32_t contig, int64_t n, const int64_t* pos, const int8_t* strand) {
+  if (!ctx || n < 0 || (n > 0 && (!pos || !strand))) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  return dm_cluster_sites_upload(ctx, contig, n, pos, strand);
+}
+
+int dm_cluster_predict(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* w, int drop_unmodified, int64_t cap,
+                       int64_t* pos, int8_t* strand, int32_t* cov, int32_t* mod, float* features, float* prob,
+                       int32_t* pct, int64_t* n_sites) {
+  if (!ctx || !w || !n_sites || !w->w1 || !w->b1 || !w->w2 || !w->b2 || !w->wo || !w->bo) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_cluster_result r;
+  DM_TRY(dm_cluster_run(ctx, contig, w, drop_unmodified, features != nullptr, r));
+  *n_sites = (int64_t)r.pos.size();
+  const size_t k = (size_t)std::min<int64_t>(cap, (int64_t)r.pos.size());
+  if (k > 0) {
+    if (pos) memcpy(pos, r.pos.data(), k * sizeof(int64_t));
+    if (strand) memcpy(strand, r.strand.data(), k);
+    if (cov) memcpy(cov, r.cov.data(), k * sizeof(int32_t));
+    if (mod) memcpy(mod, r.mod.data(), k * sizeof(int32_t));
+    if (features) memcpy(features, r.feat.data(), k * 14 * sizeof(float));
+    if (prob) memcpy(prob, r.prob.data(), k * sizeof(float));
+    if (pct) memcpy(pct, r.pct.data(), k * sizeof(int32_t));
+  }
+  return DM_OK;
+}
+
+int dm_write_cluster_bed(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* w, int drop_unmodified, const char* chrom,
+                         const char* path, int64_t* n_rows) {
+  if (!ctx || !w || !chrom || !path) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_cluster_result r;
+  DM_TRY(dm_cluster_run(ctx, contig, w, drop_unmodified, false, r));
+  if (n_rows) *n_rows = (int64_t)r.pos.size();
+  if (r.pos.empty()) return DM_OK;
+  FILE* fh = fopen(path, "w");
+  if (!fh) return fail(ctx, DM_ERR_IO, std::string("dm_write_cluster_bed: cannot open ") + path);
+  for (size_t i = 0; i < r.pos.size(); ++i) {
+    merged_line(fh, chrom, r.pos[i], ctx->base, r.strand[i] >= 0 ? '+' : '-', r.cov[i], r.mod[i]);
+    fprintf(fh, " %d\n", r.pct[i]);
+  }
+  if (fclose(fh) != 0) return fail(ctx, DM_ERR_IO, std::string("dm_write_cluster_bed: write failed for ") + path);
   return DM_OK;
 }
 

@@ -92,6 +92,7 @@ struct dm_ctx {
   std::vector<int64_t> contig_len, contig_off;   // contig_off in positions (cells / 2)
   int64_t* contig_off_d = nullptr;
   unsigned long long* cells = nullptr;           // [2][total_len] (strand-major per contig)
+  uint8_t* motif = nullptr;                      // same indexing: 1 = motif (CpG) site, for the cluster second pass
   int64_t n_cells = 0;
   char base = 'C';
   // scratch
@@ -122,6 +123,17 @@ int dm_launch_prepare(dm_ctx* ctx);                       // dm_features.cu
 int dm_launch_build_windows(dm_ctx* ctx, float* out_d);   // dm_features.cu
 int dm_launch_accumulate(dm_ctx* ctx);                    // dm_hist.cu
 int dm_launch_mask_rejected(dm_ctx* ctx);                 // dm_hist.cu
+struct dm_cluster_result {                                 // output of the cluster second pass (dm_cluster.cu)
+  std::vector<int64_t> pos;
+  std::vector<int8_t> strand;
+  std::vector<int32_t> cov, mod, pct;
+  std::vector<float> prob, feat;
+};
+int dm_cluster_run(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* cw, int drop_unmodified, bool want_feat,
+                   dm_cluster_result& out);
+int dm_cluster_sites_upload(dm_ctx* ctx, int32_t contig, int64_t n, const int64_t* pos, const int8_t* strand);
+int dm_hist_load_rows(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t n, const int64_t* pos, const int32_t* cov,
+                      const int32_t* mod);
 int dm_hist_compact(dm_ctx* ctx, int32_t contig, int8_t strand, std::vector<int64_t>& pos,
                     std::vector<int32_t>& cov, std::vector<int32_t>& mod);  // dm_hist.cu
 // BiLSTM over the uploaded batch's feature table -> b.p1 / b.pred

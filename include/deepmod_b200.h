@@ -126,6 +126,32 @@ int dm_hist_nonzero(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t cap,
 int dm_write_bed(dm_ctx* ctx, int32_t contig, int8_t strand, const char* chrom,
                  const char* path, int64_t* n_rows);
 
+/* Overwrite cells of (contig, strand) with summary rows read elsewhere (e.g. BED files of earlier runs:
+ * DeepMod_tools/sum_chr_mod.py:36-45 readbed2); deletion-touch counters of those cells become 0. */
+int dm_hist_load(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t n, const int64_t* pos,
+                 const int32_t* cov, const int32_t* mod);
+/* Merged summary of one contig in sum_chr_mod.py's format (:47-63): both strands interleaved by position,
+ * rows with mod == 0 dropped, "%s %d %d %s %d %s  %d %d 0,0,0 %d %d %d".  No file when there are no rows. */
+int dm_write_merged_bed(dm_ctx* ctx, int32_t contig, const char* chrom, const char* path, int64_t* n_rows);
+
+/* ---- CpG-cluster second pass (DeepMod_tools/hm_cluster_predict.py) ---------------------------- */
+/* MLP of train_deepmod/na12878_cluster_train_mod-*: W_1[14,100] b_1[100] W_2[100,20] b_2[20] W_O[20,1] b_O[1] */
+typedef struct dm_cluster_weights {
+  const float *w1, *b1, *w2, *b2, *wo, *bo;
+} dm_cluster_weights;
+/* Motif (CpG) sites of a contig, what the reference reads from motif_<chr>_C.bed
+ * (hm_cluster_predict.py:117-123, written by generate_motif_pos.py:56-71).  Replaces earlier sites. */
+int dm_cluster_set_sites(dm_ctx* ctx, int32_t contig, int64_t n, const int64_t* pos, const int8_t* strand);
+/* Sites = motif sites whose cell has cov > 0 (and mod > 0 when drop_unmodified, the rows sum_chr_mod.py keeps),
+ * ordered by (strand '+' first, position) like the script's sorted keys.  Outputs (any may be NULL) hold up to
+ * `cap` sites: features[cap,14] as fed to the model, prob = sigmoid output, pct = int(prob*100) (:170). */
+int dm_cluster_predict(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* w, int drop_unmodified, int64_t cap,
+                       int64_t* pos, int8_t* strand, int32_t* cov, int32_t* mod, float* features, float* prob,
+                       int32_t* pct, int64_t* n_sites);
+/* "<merged line> <pct>" per site into <prefix>_clusterCpG.<chr>.C.bed's format (:168-170). */
+int dm_write_cluster_bed(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* w, int drop_unmodified,
+                         const char* chrom, const char* path, int64_t* n_rows);
+
 /* ---- the hot path ------------------------------------------------------- */
 /* get_Feature + mPredict1 + reducer for a packed batch, host buffers in, host
  * results out.  p1_out / pred_out are indexed by window (= mapped event), reads
