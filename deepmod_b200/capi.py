@@ -12,10 +12,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdeepmod_b200.so")
 
 FP32, BF16, BF16_1CTA = 0, 1, 2
-READ_OK, READ_MISMATCH, READ_BAD_ALIGN, READ_LESS_EVENT = 0, 1, 2, 3
+READ_OK, READ_MISMATCH, READ_BAD_ALIGN, READ_LESS_EVENT, READ_NO_MATCH = 0, 1, 2, 3, 4
 STATUS_TEXT = {READ_OK: "", READ_MISMATCH: "Error Does not match",      # myDetect.py:870
                READ_BAD_ALIGN: "Error alignment/event count mismatch",
-               READ_LESS_EVENT: "Less Event"}                           # myDetect.py:704
+               READ_LESS_EVENT: "Less Event",                          # myDetect.py:704
+               READ_NO_MATCH: "no first and/or last match"}             # myDetect.py:622-627
 WINDOW, FNUM, HIDDEN = 21, 7, 100
 TC_DUMP_BYTES = 137216 + 8 * 8192
 
@@ -35,6 +36,13 @@ class DmBatch(C.Structure):
                 ("ev_off", _i64p), ("ev_mean", _fp), ("ev_stdv", _fp), ("ev_len", _fp), ("ev_base", _u8p),
                 ("col_off", _i64p), ("col_refbase", _u8p), ("col_readbase", _u8p), ("col_refpos", _i64p),
                 ("start_clip", _i32p), ("end_clip", _i32p), ("contig", _i32p), ("strand", _i8p)]
+
+
+class DmSamBatch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("ev_off", _i64p), ("ev_mean", _fp), ("ev_stdv", _fp), ("ev_len", _fp),
+                ("ev_base", _u8p), ("contig", _i32p), ("strand", _i8p), ("ref_start", _i64p), ("clip_left", _i32p),
+                ("clip_right", _i32p), ("op_off", _i64p), ("op_code", _u8p), ("op_len", _i32p), ("seq_off", _i64p),
+                ("seq", _u8p)]
 
 
 class DmClusterWeights(C.Structure):
@@ -60,6 +68,9 @@ SIGNATURES = {
     "dm_hist_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _i64p]),
     "dm_hist_nonzero": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _i64p, _i32p, _i32p, _i64p]),
     "dm_write_bed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_char_p, C.c_char_p, _i64p]),
+    "dm_set_contig_sequence": (C.c_int, [C.c_void_p, C.c_int32, _u8p, C.c_int64]),
+    "dm_align_upload": (C.c_int, [C.c_void_p, C.POINTER(DmSamBatch), _i64p, _i64p]),
+    "dm_fetch_alignment": (C.c_int, [C.c_void_p, _i64p, _u8p, _u8p, _i64p, _i32p, _i32p]),
     "dm_hist_load": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _i64p, _i32p, _i32p]),
     "dm_write_merged_bed": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p, _i64p]),
     "dm_cluster_set_sites": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, _i64p, _i8p]),
@@ -341,6 +352,38 @@ class Context(object):
         self._check(self.lib.dm_detect_batch(self._h, C.byref(pb.struct), _ptr(p1, C.c_float), _ptr(pred, C.c_uint8),
                                              _ptr(status, C.c_int32)), "dm_detect_batch")
         return p1, pred, status
+
+    # -- from SAM records ------------------------------------------------------------------------
+    def set_contig_sequence(self, contig, seq):
+        seq = _arr(seq, np.uint8)
+        self._check(self.lib.dm_set_contig_sequence(self._h, contig, _ptr(seq, C.c_uint8), len(seq)), "dm_set_contig_sequence")
+
+    SAM_FIELDS = (("ev_off", np.int64), ("ev_mean", np.float32), ("ev_stdv", np.float32), ("ev_len", np.float32),
+                  ("ev_base", np.uint8), ("contig", np.int32), ("strand", np.int8), ("ref_start", np.int64),
+                  ("clip_left", np.int32), ("clip_right", np.int32), ("op_off", np.int64), ("op_code", np.uint8),
+                  ("op_len", np.int32), ("seq_off", np.int64), ("seq", np.uint8))
+
+    def align_upload(self, arrays):
+        """CIGAR walk on the GPU; the batch is then resident (detect_resident / fetch).  -> (n_windows, n_cols)"""
+        keep = {k: _arr(arrays[k], dt) for k, dt in self.SAM_FIELDS}
+        ct = {np.int64: C.c_int64, np.float32: C.c_float, np.uint8: C.c_uint8, np.int32: C.c_int32, np.int8: C.c_int8}
+        sb = DmSamBatch()
+        sb.n_reads = len(keep["contig"])
+        for k, dt in self.SAM_FIELDS:
+            setattr(sb, k, _ptr(keep[k], ct[dt]))
+        nw, nc = C.c_int64(), C.c_int64()
+        self._check(self.lib.dm_align_upload(self._h, C.byref(sb), C.byref(nw), C.byref(nc)), "dm_align_upload")
+        self._resident_reads = sb.n_reads
+        return nw.value, nc.value
+
+    def fetch_alignment(self, n_reads, n_cols):
+        col_off = np.zeros(n_reads + 1, np.int64)
+        refb, readb, refpos = np.zeros(n_cols, np.uint8), np.zeros(n_cols, np.uint8), np.zeros(n_cols, np.int64)
+        sc, ec = np.zeros(n_reads, np.int32), np.zeros(n_reads, np.int32)
+        self._check(self.lib.dm_fetch_alignment(self._h, _ptr(col_off, C.c_int64), _ptr(refb, C.c_uint8), _ptr(readb, C.c_uint8),
+                                                _ptr(refpos, C.c_int64), _ptr(sc, C.c_int32), _ptr(ec, C.c_int32)),
+                    "dm_fetch_alignment")
+        return dict(col_off=col_off, col_refbase=refb, col_readbase=readb, col_refpos=refpos, start_clip=sc, end_clip=ec)
 
     def upload(self, batch):
         pb = batch if isinstance(batch, PackedBatch) else PackedBatch(batch)

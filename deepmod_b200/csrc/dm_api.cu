@@ -170,10 +170,10 @@ void dm_destroy(dm_ctx* ctx) {
     cudaFree(b->ev_base); cudaFree(b->col_refbase); cudaFree(b->col_readbase);
     cudaFree(b->start_clip); cudaFree(b->end_clip); cudaFree(b->contig); cudaFree(b->strand);
     cudaFree(b->win_off); cudaFree(b->col_rank); cudaFree(b->win_col); cudaFree(b->win_frow);
-    cudaFree(b->status); cudaFree(b->feat); cudaFree(b->feat_tc); cudaFree(b->p1); cudaFree(b->pred);
+    cudaFree(b->status); cudaFree(b->align_status); cudaFree(b->feat); cudaFree(b->feat_tc); cudaFree(b->p1); cudaFree(b->pred);
   }
   cudaFree(ctx->fw_x);
-  cudaFree(ctx->contig_off_d); cudaFree(ctx->cells); cudaFree(ctx->motif);
+  cudaFree(ctx->contig_off_d); cudaFree(ctx->cells); cudaFree(ctx->motif); cudaFree(ctx->genome);
   cudaFree(ctx->scratch); cudaFree(ctx->hbuf); cudaFree(ctx->dpart);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -234,7 +234,69 @@ int reserve_windows(dm_ctx* ctx, dm_dev_batch& b, int64_t n_windows, int64_t n_f
 
 }  // namespace
 
+int dm_batch_reserve(dm_ctx* ctx, int64_t n, int64_t n_events, int64_t n_cols, int64_t n_windows) {
+  dm_dev_batch& b = ctx->b;
+  if (n > b.cap_reads) {
+    const int64_t cap = n + n / 8 + 16;
+    DM_TRY(grow(ctx, b.ev_off, cap + 1)); DM_TRY(grow(ctx, b.col_off, cap + 1)); DM_TRY(grow(ctx, b.win_off, cap + 1));
+    DM_TRY(grow(ctx, b.start_clip, cap)); DM_TRY(grow(ctx, b.end_clip, cap)); DM_TRY(grow(ctx, b.contig, cap));
+    DM_TRY(grow(ctx, b.strand, cap)); DM_TRY(grow(ctx, b.status, cap)); DM_TRY(grow(ctx, b.align_status, cap));
+    b.cap_reads = cap;
+  }
+  if (n_events > b.cap_events) {
+    const int64_t cap = n_events + n_events / 8;
+    DM_TRY(grow(ctx, b.ev_mean, cap)); DM_TRY(grow(ctx, b.ev_stdv, cap)); DM_TRY(grow(ctx, b.ev_len, cap));
+    DM_TRY(grow(ctx, b.ev_base, cap));
+    b.cap_events = cap;
+  }
+  if (n_cols > b.cap_cols) {
+    const int64_t cap = n_cols + n_cols / 8;
+    DM_TRY(grow(ctx, b.col_refbase, cap)); DM_TRY(grow(ctx, b.col_readbase, cap)); DM_TRY(grow(ctx, b.col_refpos, cap));
+    DM_TRY(grow(ctx, b.col_rank, cap));
+    b.cap_cols = cap;
+  }
+  return reserve_windows(ctx, b, n_windows, n_windows + (int64_t)(2 * DM_FLANK) * n);
+}
+
 extern "C" {
+
+int dm_set_contig_sequence(dm_ctx* ctx, int32_t contig, const uint8_t* seq, int64_t len) {
+  if (!ctx || !seq || len < 0) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  return dm_genome_sequence_upload(ctx, contig, seq, len);
+}
+
+int dm_align_upload(dm_ctx* ctx, const dm_sam_batch* sb, int64_t* n_windows, int64_t* n_cols) {
+  if (!ctx || !sb) return DM_ERR_ARG;
+  if (sb->n_reads < 0) return fail(ctx, DM_ERR_ARG, "dm_align_upload: negative n_reads");
+  if (sb->n_reads > 0 && (!sb->ev_off || !sb->contig || !sb->strand || !sb->ref_start || !sb->clip_left || !sb->clip_right ||
+                          !sb->op_off || !sb->op_code || !sb->op_len || !sb->seq_off || !sb->seq || !sb->ev_mean ||
+                          !sb->ev_stdv || !sb->ev_len))
+    return fail(ctx, DM_ERR_ARG, "dm_align_upload: null array");
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  return dm_align_build(ctx, sb, n_windows, n_cols);
+}
+
+int dm_fetch_alignment(dm_ctx* ctx, int64_t* col_off, uint8_t* refbase, uint8_t* readbase, int64_t* refpos,
+                       int32_t* start_clip, int32_t* end_clip) {
+  if (!ctx) return DM_ERR_ARG;
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  dm_dev_batch& b = ctx->b;
+  cudaStream_t s = ctx->stream;
+  const auto D2H = cudaMemcpyDeviceToHost;
+  if (b.n_reads > 0) {
+    if (col_off) DM_CUDA(ctx, cudaMemcpyAsync(col_off, b.col_off, sizeof(int64_t) * (b.n_reads + 1), D2H, s));
+    if (start_clip) DM_CUDA(ctx, cudaMemcpyAsync(start_clip, b.start_clip, sizeof(int32_t) * b.n_reads, D2H, s));
+    if (end_clip) DM_CUDA(ctx, cudaMemcpyAsync(end_clip, b.end_clip, sizeof(int32_t) * b.n_reads, D2H, s));
+  }
+  if (b.n_cols > 0) {
+    if (refbase) DM_CUDA(ctx, cudaMemcpyAsync(refbase, b.col_refbase, b.n_cols, D2H, s));
+    if (readbase) DM_CUDA(ctx, cudaMemcpyAsync(readbase, b.col_readbase, b.n_cols, D2H, s));
+    if (refpos) DM_CUDA(ctx, cudaMemcpyAsync(refpos, b.col_refpos, sizeof(int64_t) * b.n_cols, D2H, s));
+  }
+  DM_CUDA(ctx, cudaStreamSynchronize(s));
+  return DM_OK;
+}
 
 int dm_batch_upload(dm_ctx* ctx, const dm_batch* hb, int64_t* n_windows_out) {
   if (!ctx || !hb) return DM_ERR_ARG;
@@ -264,26 +326,8 @@ int dm_batch_upload(dm_ctx* ctx, const dm_batch* hb, int64_t* n_windows_out) {
   if (n_frows + DM_WINDOW >= (int64_t)INT32_MAX) return fail(ctx, DM_ERR_ARG, "dm_batch_upload: batch too large (>2^31 rows)");
   if (n_events > 0 && (!hb->ev_mean || !hb->ev_stdv || !hb->ev_len)) return fail(ctx, DM_ERR_ARG, "dm_batch_upload: null event array");
   if (n_cols > 0 && (!hb->col_refbase || !hb->col_readbase || !hb->col_refpos)) return fail(ctx, DM_ERR_ARG, "dm_batch_upload: null column array");
-  if (n > b.cap_reads) {
-    const int64_t cap = n + n / 8 + 16;
-    DM_TRY(grow(ctx, b.ev_off, cap + 1)); DM_TRY(grow(ctx, b.col_off, cap + 1)); DM_TRY(grow(ctx, b.win_off, cap + 1));
-    DM_TRY(grow(ctx, b.start_clip, cap)); DM_TRY(grow(ctx, b.end_clip, cap)); DM_TRY(grow(ctx, b.contig, cap));
-    DM_TRY(grow(ctx, b.strand, cap)); DM_TRY(grow(ctx, b.status, cap));
-    b.cap_reads = cap;
-  }
-  if (n_events > b.cap_events) {
-    const int64_t cap = n_events + n_events / 8;
-    DM_TRY(grow(ctx, b.ev_mean, cap)); DM_TRY(grow(ctx, b.ev_stdv, cap)); DM_TRY(grow(ctx, b.ev_len, cap));
-    DM_TRY(grow(ctx, b.ev_base, cap));
-    b.cap_events = cap;
-  }
-  if (n_cols > b.cap_cols) {
-    const int64_t cap = n_cols + n_cols / 8;
-    DM_TRY(grow(ctx, b.col_refbase, cap)); DM_TRY(grow(ctx, b.col_readbase, cap)); DM_TRY(grow(ctx, b.col_refpos, cap));
-    DM_TRY(grow(ctx, b.col_rank, cap));
-    b.cap_cols = cap;
-  }
-  DM_TRY(reserve_windows(ctx, b, n_windows, n_frows));
+  DM_TRY(dm_batch_reserve(ctx, n, n_events, n_cols, n_windows));
+  b.from_alignment = false;
   cudaStream_t s = ctx->stream;
   const auto H2D = cudaMemcpyHostToDevice;
   DM_CUDA(ctx, cudaMemcpyAsync(b.ev_off, hb->ev_off, sizeof(int64_t) * (n + 1), H2D, s));
@@ -348,6 +392,12 @@ int dm_fetch_results(dm_ctx* ctx, float* p1_out, uint8_t* pred_out, int32_t* sta
   if (pred_out && b.n_windows > 0) DM_CUDA(ctx, cudaMemcpyAsync(pred_out, b.pred, b.n_windows, D2H, s));
   if (status_out && b.n_reads > 0) DM_CUDA(ctx, cudaMemcpyAsync(status_out, b.status, sizeof(int32_t) * b.n_reads, D2H, s));
   DM_CUDA(ctx, cudaStreamSynchronize(s));
+  if (status_out && b.n_reads > 0 && b.from_alignment) {     // a read dropped by the CIGAR walk keeps that verdict
+    std::vector<int32_t> al((size_t)b.n_reads);
+    DM_CUDA(ctx, cudaMemcpy(al.data(), b.align_status, sizeof(int32_t) * b.n_reads, D2H));
+    for (int r = 0; r < b.n_reads; ++r)
+      if (al[r] != DM_READ_OK) status_out[r] = al[r];
+  }
   return DM_OK;
 }
 
@@ -420,6 +470,7 @@ int dm_set_genome(dm_ctx* ctx, int32_t n_contigs, const int64_t* contig_len, cha
   }
   cudaFree(ctx->cells); ctx->cells = nullptr;
   cudaFree(ctx->motif); ctx->motif = nullptr;
+  cudaFree(ctx->genome); ctx->genome = nullptr;
   cudaFree(ctx->contig_off_d); ctx->contig_off_d = nullptr;
   ctx->n_cells = 2 * off[n_contigs];
   DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->cells), sizeof(unsigned long long) * (size_t)std::max<int64_t>(ctx->n_cells, 1)));

@@ -66,6 +66,7 @@ struct dm_dev_batch {
   int64_t *win_col = nullptr;     // [n_windows] alignment column of each window centre (-1: none)
   int32_t *win_frow = nullptr;    // [n_windows_padded] first feature row of each window
   int32_t *status = nullptr;      // [n_reads]
+  int32_t *align_status = nullptr;  // [n_reads] verdict of the CIGAR walk (dm_align_upload), merged into status on fetch
   float *feat = nullptr;          // [n_frows+21][8] fp32 feature rows (+21 all-zero rows)
   __nv_bfloat16* feat_tc = nullptr;  // [n_frows+21][16] bf16 hi/lo rows for the tensor-core path
   float *p1 = nullptr;            // [n_windows_padded]
@@ -74,6 +75,7 @@ struct dm_dev_batch {
   int64_t cap_reads = 0, cap_events = 0, cap_cols = 0, cap_windows = 0, cap_frows = 0;
   bool has_ev_base = false;
   bool prepared = false;          // derived arrays are current for the uploaded inputs
+  bool from_alignment = false;    // columns were produced by dm_align_upload
 };
 
 struct dm_ctx {
@@ -92,6 +94,7 @@ struct dm_ctx {
   std::vector<int64_t> contig_len, contig_off;   // contig_off in positions (cells / 2)
   int64_t* contig_off_d = nullptr;
   unsigned long long* cells = nullptr;           // [2][total_len] (strand-major per contig)
+  uint8_t* genome = nullptr;                     // [total_len] reference bases (dm_set_contig_sequence)
   uint8_t* motif = nullptr;                      // same indexing: 1 = motif (CpG) site, for the cluster second pass
   int64_t n_cells = 0;
   char base = 'C';
@@ -119,6 +122,9 @@ void dm_set_error(dm_ctx* ctx, const std::string& msg);
   } while (0)
 
 // kernels / launchers (each returns a dm_status) ---------------------------------
+int dm_batch_reserve(dm_ctx* ctx, int64_t n_reads, int64_t n_events, int64_t n_cols, int64_t n_windows);  // dm_api.cu
+int dm_genome_sequence_upload(dm_ctx* ctx, int32_t contig, const uint8_t* seq, int64_t len);               // dm_align.cu
+int dm_align_build(dm_ctx* ctx, const dm_sam_batch* sb, int64_t* n_windows_out, int64_t* n_cols_out);      // dm_align.cu
 int dm_launch_prepare(dm_ctx* ctx);                       // dm_features.cu
 int dm_launch_build_windows(dm_ctx* ctx, float* out_d);   // dm_features.cu
 int dm_launch_accumulate(dm_ctx* ctx);                    // dm_hist.cu

@@ -25,7 +25,7 @@ import time
 
 import numpy as np
 
-from . import capi, checkpoint, reads_io, synth
+from . import capi, checkpoint, reads_io, sam, synth
 
 OUTPUT_DEBUG, OUTPUT_INFO, OUTPUT_WARNING, OUTPUT_ERROR = 0, 1, 2, 3     # myCom.py:5-8
 MAX_WINDOWS_PER_CALL = 16 * 1024 * 1024
@@ -121,6 +121,61 @@ def detect_handler(moptions, ctx, read_files, contig_names, failed):
     return n_reads, n_windows
 
 
+def find_sam_files(wrk_base, recursive=1):
+    """<name>.sam files that have a <name>.events.npz next to them."""
+    files = glob.glob(os.path.join(wrk_base, "*.sam"))
+    if recursive == 1:
+        for depth in ("*", "*/*", "*/*/*"):
+            files.extend(glob.glob(os.path.join(wrk_base, depth, "*.sam")))
+    return sorted(f for f in files if os.path.isfile(f[:-4] + ".events.npz"))
+
+
+def detect_handler_sam(moptions, ctx, sam_files, contig_names, failed):
+    """Same worker for SAM-level input: the CIGAR walk of handle_record (:488-705) runs on the GPU too."""
+    world, rank, _ = _dist_env()
+    n_reads = n_windows = 0
+    for path in sam_files:
+        reads = reads_io.load_events(path[:-4] + ".events.npz")
+        with open(path) as fh:
+            lines = fh.read().splitlines()
+        arrays, qnames, skipped = sam.tokenise(lines, reads, contig_names, moptions)
+        for q, why in skipped.items():
+            if why not in ("outside region", "unknown chromosome"):
+                failed.setdefault(why, []).append(q)
+        if world > 1:                                   # contiguous ranges balanced by events
+            ev = np.diff(arrays["ev_off"])
+            cum = np.cumsum(ev)
+            total = int(cum[-1]) if len(cum) else 0
+            lo = int(np.searchsorted(cum, total * rank / world, side="right")) if rank else 0
+            hi = int(np.searchsorted(cum, total * (rank + 1) / world, side="right")) if rank + 1 < world else len(ev)
+            arrays = sam_take(arrays, lo, hi)
+            qnames = qnames[lo:hi]
+        n_win, _ = ctx.align_upload(arrays)
+        ctx.detect_resident(True)
+        _, _, status = ctx.fetch(n_win, len(qnames))
+        n_reads += len(qnames)
+        for code in np.unique(status):
+            if code != capi.READ_OK:
+                failed.setdefault(capi.STATUS_TEXT[int(code)], []).extend(qnames[int(i)] for i in np.flatnonzero(status == code))
+        n_windows += n_win
+    return n_reads, n_windows
+
+
+def sam_take(arrays, lo, hi):
+    """Reads [lo, hi) of a tokenised SAM batch."""
+    out = {}
+    for off_key, keys in (("ev_off", ("ev_mean", "ev_stdv", "ev_len", "ev_base")), ("op_off", ("op_code", "op_len")),
+                          ("seq_off", ("seq",))):
+        off = arrays[off_key]
+        a, b = int(off[lo]), int(off[hi])
+        for k in keys:
+            out[k] = arrays[k][a:b]
+        out[off_key] = (off[lo:hi + 1] - off[lo]).astype(np.int64)
+    for k in ("contig", "strand", "ref_start", "clip_left", "clip_right"):
+        out[k] = arrays[k][lo:hi]
+    return out
+
+
 def sum_handler(moptions, ctx, contig_names):
     """Write one BED per (chr, strand) that has at least one position (:1107-1120)."""
     written = []
@@ -149,10 +204,13 @@ def mDetect_manager(moptions):
 
     start_time = time.time()
     read_files = find_read_files(moptions["wrkBase"], moptions.get("recursive", 1))
+    sam_files = find_sam_files(moptions["wrkBase"], moptions.get("recursive", 1))
     if rank == 0:
-        print("Total files=%d" % len(read_files))
-    if not read_files:
-        raise capi.DeepModError("no %s files under %s" % (READS_GLOB, moptions["wrkBase"]))
+        print("Total files=%d" % (len(read_files) + len(sam_files)))
+    if not read_files and not sam_files:
+        raise capi.DeepModError("no %s or *.sam + *.events.npz files under %s" % (READS_GLOB, moptions["wrkBase"]))
+    if sam_files and not moptions.get("Ref"):
+        raise capi.DeepModError("SAM input needs --Ref (the reference FASTA)")
     out_dir = moptions["outFolder"] + moptions["FileID"]
     if rank == 0:
         os.makedirs(out_dir, exist_ok=True)                                         # :1151-1152
@@ -165,11 +223,21 @@ def mDetect_manager(moptions):
             torch.cuda.set_device(local)
             dist.init_process_group("nccl")
     precision = capi.BF16 if str(moptions.get("precision", "fp32")).lower() in ("bf16", "1") else capi.FP32
-    _, contig_names, contig_len = reads_io.load_reads(read_files[0], header_only=True)
+    ref_seqs = None
+    if sam_files:
+        contig_names, ref_seqs = reads_io.read_fasta(moptions["Ref"])
+        contig_len = np.array([len(x) for x in ref_seqs], np.int64)
+    else:
+        _, contig_names, contig_len = reads_io.load_reads(read_files[0], header_only=True)
     failed = {}
     with capi.Context(model, device=local, precision=precision) as ctx:
         ctx.set_genome(contig_len, moptions["Base"])
-        n_reads, n_windows = detect_handler(moptions, ctx, read_files, contig_names, failed)
+        n_reads, n_windows = detect_handler(moptions, ctx, read_files, contig_names, failed) if read_files else (0, 0)
+        if sam_files:
+            for ci, seq in enumerate(ref_seqs):
+                ctx.set_contig_sequence(ci, seq)
+            nr, nw = detect_handler_sam(moptions, ctx, sam_files, contig_names, failed)
+            n_reads, n_windows = n_reads + nr, n_windows + nw
         if world > 1:
             import torch
             cells = ctx.hist_tensor()

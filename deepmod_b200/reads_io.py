@@ -29,3 +29,48 @@ def load_reads(path, header_only=False):
             return None, names, lens
         batch = {k: z[k] for k in BATCH_KEYS if k in z.files}
     return batch, names, lens
+
+
+# ---------------------------------------------------------------------------------------------------
+# SAM-level input: <name>.sam next to <name>.events.npz, plus the --Ref FASTA
+
+def save_events(path, reads):
+    """reads: {qname: dict(ev_mean, ev_stdv, ev_len, ev_base)} -> <name>.events.npz (event tables of
+    getEvent / mnormalized, myDetect.py:133-343, flattened)."""
+    if not path.endswith(".events.npz"):
+        raise ValueError("event tables are named *.events.npz")
+    q = list(reads)
+    off = np.concatenate([[0], np.cumsum([len(reads[k]["ev_mean"]) for k in q])]).astype(np.int64)
+    cat = lambda key, dt: (np.concatenate([np.asarray(reads[k][key]) for k in q]).astype(dt) if q else np.zeros(0, dt))
+    with open(path, "wb") as fh:
+        np.savez(fh, qnames=np.array(q), ev_off=off, ev_mean=cat("ev_mean", np.float32), ev_stdv=cat("ev_stdv", np.float32),
+                 ev_len=cat("ev_len", np.float32), ev_base=cat("ev_base", np.uint8))
+
+
+def load_events(path):
+    with np.load(path, allow_pickle=False) as z:
+        q = [str(x) for x in z["qnames"]]
+        off = z["ev_off"]
+        return {k: dict(ev_mean=z["ev_mean"][off[i]:off[i + 1]], ev_stdv=z["ev_stdv"][off[i]:off[i + 1]],
+                        ev_len=z["ev_len"][off[i]:off[i + 1]], ev_base=z["ev_base"][off[i]:off[i + 1]])
+                for i, k in enumerate(q)}
+
+
+def read_fasta(path):
+    """-> (names, [uint8 upper-case sequence]) ; what `samtools faidx` + .upper() gives getRefSeq (myDetect.py:470-483)."""
+    names, seqs, cur = [], [], []
+    with open(path) as fh:
+        for line in fh:
+            line = line.strip()
+            if not line:
+                continue
+            if line[0] == ">":
+                if names:
+                    seqs.append(np.frombuffer("".join(cur).upper().encode(), np.uint8))
+                names.append(line[1:].split()[0])
+                cur = []
+            else:
+                cur.append(line)
+    if names:
+        seqs.append(np.frombuffer("".join(cur).upper().encode(), np.uint8))
+    return names, seqs

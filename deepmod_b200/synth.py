@@ -199,3 +199,89 @@ def concat_batches(parts):
         lens = np.concatenate([np.diff(p[k]) for p in parts])
         out[k] = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# SAM-level synthetic reads: input of the alignment walk (myDetect.py:929-943, :488-705)
+
+def _revcomp(a):
+    return _COMP[a[::-1]]
+
+
+def _rle_cigar(ops):
+    out, i = [], 0
+    while i < len(ops):
+        j = i
+        while j < len(ops) and ops[j] == ops[i]:
+            j += 1
+        out.append("%d%s" % (j - i, ops[i]))
+        i = j
+    return "".join(out)
+
+
+def make_sam_reads(genome, contig_names, n_reads, seed=5, mean_len=800, len_lo=80, len_hi=20000, extended_cigar=0.3,
+                   p_secondary=0.3, p_hardclip=0.2, p_edge_mismatch=0.3):
+    """-> (sam_lines, reads) where reads[qname] = dict(ev_mean, ev_stdv, ev_len, ev_base [uint8 ASCII]).
+
+    SEQ is in reference orientation (reverse-complemented for flag 16) while the event table is in sequencing
+    order, as in a real run.  Covers: soft/hard clips, leading/trailing insertions, '=' / 'X' CIGARs, first/last
+    aligned columns that are mismatches, secondary records with lower and higher MAPQ, unmapped records."""
+    rng = np.random.default_rng(seed)
+    lines = ["@HD\tVN:1.6", ""]
+    reads = {}
+    for r in range(n_reads):
+        q = "read%04d" % r
+        ci = int(rng.integers(0, len(genome)))
+        g = genome[ci]
+        L = int(np.clip(rng.gamma(2.0, mean_len / 2.0), len_lo, len_hi))
+        ext = rng.random() < extended_cigar
+        ncol = L + 40
+        u = rng.random(ncol)
+        typ = np.zeros(ncol, np.int8)
+        typ[u < 0.08] = 1; typ[u < 0.05] = 2; typ[u < 0.025] = 3
+        if rng.random() < p_edge_mismatch:
+            typ[0] = 1
+        else:
+            typ[0] = 0
+        typ[-1] = 1 if rng.random() < p_edge_mismatch else 0
+        span = int(np.count_nonzero(typ != 2))
+        start = int(rng.integers(0, len(g) - span - 1))
+        adv = (typ != 2).astype(np.int64)
+        pos = start + np.cumsum(adv) - adv
+        refb = g[np.minimum(pos, len(g) - 1)]
+        readb = refb.copy()
+        mm = np.flatnonzero(typ == 1)
+        readb[mm] = _ASCII[(np.searchsorted(_ASCII, refb[mm]) + rng.integers(1, 4, size=len(mm))) % 4]
+        ins = np.flatnonzero(typ == 2)
+        readb[ins] = _ASCII[rng.integers(0, 4, size=len(ins))]
+        aligned = readb[typ != 3]
+        ops = np.array(["M", "M", "I", "D"])[typ] if not ext else np.array(["=", "X", "I", "D"])[typ]
+        lead_ins = int(rng.integers(0, 4)) if rng.random() < 0.3 else 0          # "5S3I..." : leading insertion
+        sl, sr = int(rng.integers(0, 25)), int(rng.integers(0, 25))
+        hl, hr = (int(rng.integers(1, 10)), int(rng.integers(1, 10))) if rng.random() < p_hardclip else (0, 0)
+        if hl:
+            sl = sr = 0                                                          # hard-clipped records carry no soft clip here
+        rnd = lambda k: _ASCII[rng.integers(0, 4, size=k)]
+        seq = np.concatenate([rnd(sl), rnd(lead_ins), aligned, rnd(sr)])
+        cigar = ("%dH" % hl if hl else "") + ("%dS" % sl if sl else "") + ("%dI" % lead_ins if lead_ins else "") + \
+            _rle_cigar(list(ops)) + ("%dS" % sr if sr else "") + ("%dH" % hr if hr else "")
+        full = np.concatenate([rnd(hl), seq, rnd(hr)])                           # what was actually sequenced (reference orientation)
+        strand_rev = rng.random() < 0.5
+        ev_base = _revcomp(full) if strand_rev else full
+        n_ev = len(full)
+        reads[q] = dict(ev_mean=np.round(np.clip(rng.normal(0, 1.4, n_ev), -5, 5), 3).astype(np.float32),
+                        ev_stdv=np.round(np.abs(rng.normal(0.25, 0.12, n_ev)), 3).astype(np.float32),
+                        ev_len=(2 + rng.geometric(0.12, n_ev)).astype(np.float32), ev_base=ev_base.copy())
+        flag = 16 if strand_rev else 0
+        mapq = int(rng.integers(5, 60))
+        main = "\t".join([q, str(flag), contig_names[ci], str(start + 1), str(mapq), cigar, "*", "0", "0",
+                          seq.tobytes().decode(), "*"])
+        recs = [main]
+        if rng.random() < p_secondary:                                           # worse record elsewhere: must lose
+            recs.insert(int(rng.integers(0, 2)), "\t".join([q, str(flag | 256), contig_names[ci], str(int(rng.integers(1, 1000))),
+                                                            str(mapq - 1 if mapq > 0 else 0), "%dM" % len(seq), "*", "0", "0",
+                                                            seq.tobytes().decode(), "*"]))
+        if rng.random() < 0.1:
+            recs.append("\t".join([q, "4", "*", "0", "0", "*", "*", "0", "0", seq.tobytes().decode(), "*"]))
+        lines.extend(recs)
+    return lines, reads

@@ -59,7 +59,8 @@ enum dm_read_status {
   DM_READ_OK = 0,
   DM_READ_MISMATCH = 1,    /* 'Error Does not match', myDetect.py:868-874 */
   DM_READ_BAD_ALIGN = 2,   /* #non-gap columns != mapped events (reference would raise) */
-  DM_READ_LESS_EVENT = 3   /* 'Less Event', myDetect.py:702-705 */
+  DM_READ_LESS_EVENT = 3,  /* 'Less Event', myDetect.py:702-705 */
+  DM_READ_NO_MATCH = 4     /* alignment without a single matching base, myDetect.py:622-627 (dm_align_upload only) */
 };
 
 /* The 14 inference tensors exactly as Saver.restore leaves them (fp32, row-major):
@@ -159,6 +160,44 @@ int dm_write_cluster_bed(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* 
  * status_out[n_reads] receives dm_read_status.  Any output may be NULL. */
 int dm_detect_batch(dm_ctx* ctx, const dm_batch* b, float* p1_out, uint8_t* pred_out,
                     int32_t* status_out);
+
+/* ---- from alignment records (SAM) instead of ready-made columns ---------------------------------------- */
+/* Reference sequence of a contig (upper-case ASCII, length = the contig length given to dm_set_genome); what
+ * getRefSeq fetches with `samtools faidx` (myDetect.py:470-483). */
+int dm_set_contig_sequence(dm_ctx* ctx, int32_t contig, const uint8_t* seq, int64_t len);
+
+/* One best-MAPQ record per read (handle_line, myDetect.py:929-943) after the removal of leading / trailing
+ * non-aligned CIGAR ops (:527-540), tokenised by the host (deepmod_b200/sam.py):
+ *   clip_left/right  bases clipped at the alignment's left / right end (S, H, leading I, X ...), :527-540
+ *   ref_start        0-based reference position of the first remaining op
+ *   op_code/op_len   remaining ops, ASCII codes out of "MIDNSHP=X"; op_off[r]..op_off[r+1] per read
+ *   seq              SEQ without the clipped bases (reference orientation); seq_off per read
+ * Event arrays as in dm_batch (sequencing order). */
+typedef struct dm_sam_batch {
+  int32_t        n_reads;
+  const int64_t* ev_off;
+  const float*   ev_mean;
+  const float*   ev_stdv;
+  const float*   ev_len;
+  const uint8_t* ev_base;
+  const int32_t* contig;
+  const int8_t*  strand;       /* +1 / -1 (flag & 0x10) */
+  const int64_t* ref_start;
+  const int32_t* clip_left;
+  const int32_t* clip_right;
+  const int64_t* op_off;       /* [n_reads+1] */
+  const uint8_t* op_code;
+  const int32_t* op_len;
+  const int64_t* seq_off;      /* [n_reads+1] */
+  const uint8_t* seq;
+} dm_sam_batch;
+/* The CIGAR walk of handle_record (myDetect.py:565-705) on the GPU; leaves the batch resident exactly as
+ * dm_batch_upload would (then dm_detect_resident / dm_fetch_results). */
+int dm_align_upload(dm_ctx* ctx, const dm_sam_batch* sb, int64_t* n_windows, int64_t* n_cols);
+/* The alignment columns of the resident batch (= base_map_info): col_off[n_reads+1], columns, final clips in read
+ * orientation.  Any pointer may be NULL. */
+int dm_fetch_alignment(dm_ctx* ctx, int64_t* col_off, uint8_t* refbase, uint8_t* readbase, int64_t* refpos,
+                       int32_t* start_clip, int32_t* end_clip);
 
 /* Same work with the batch resident in HBM: upload once, run many times. */
 int dm_batch_upload(dm_ctx* ctx, const dm_batch* b, int64_t* n_windows);
