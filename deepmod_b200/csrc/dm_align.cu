@@ -72,11 +72,13 @@ __global__ void k_expand(int64_t n_raw, int64_t n_ops, int n_reads, const int64_
   raw_pos[c] = rp;
   const bool match = op == '=' || (op == 'M' && rb == qb);
   if (match) {
+    // columns are ordered inside a read, so only the first / last matching lane of a same-read run in the warp
+    // can improve the read's minimum / maximum
     const int col = (int)(c - op_col[op_off[r]]);
-    atomicMin(&acc[r].first_read, (int)ri);
-    atomicMax(&acc[r].last_read, (int)ri);
-    atomicMin(&acc[r].first_col, col);
-    atomicMax(&acc[r].last_col, col);
+    const unsigned peers = __match_any_sync(__activemask(), r);
+    const int lane = threadIdx.x & 31;
+    if (lane == __ffs(peers) - 1) { atomicMin(&acc[r].first_read, (int)ri); atomicMin(&acc[r].first_col, col); }
+    if (lane == 31 - __clz(peers)) { atomicMax(&acc[r].last_read, (int)ri); atomicMax(&acc[r].last_col, col); }
   }
 }
 
@@ -139,31 +141,35 @@ __global__ void k_emit_columns(int64_t n_out, int n_reads, const int64_t* __rest
   }
 }
 
-// one thread per read, sequential like the reference loop (:680-700): later decisions see earlier swaps
-__global__ void k_gap_swap(int n_reads, const int64_t* __restrict__ col_off, const uint8_t* __restrict__ refb,
+// CpG gap swap (:680-700), one thread per column.  The reference walks the columns sequentially, but a swap of the
+// first rule only rewrites G-reference columns behind a (C,C) column and a swap of the second rule only rewrites
+// C-reference columns in front of a (G,G) column; neither can create, destroy or feed a trigger of the other kind or
+// of a later one of its own kind, so every trigger can be decided on its own and the swaps never overlap.
+__global__ void k_gap_swap(int64_t n_out, int n_reads, const int64_t* __restrict__ col_off, const uint8_t* __restrict__ refb,
                            uint8_t* __restrict__ readb) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_reads) return;
-  const int64_t b = col_off[r], n = col_off[r + 1] - b;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_out) return;
+  const uint8_t rfc = refb[c], rdc = readb[c];
+  const bool t1 = rfc == 'C' && rdc == 'C', t2 = rfc == 'G' && rdc == 'G';
+  if (!t1 && !t2) return;
+  const int r = find_seg(col_off, n_reads, c);
+  const int64_t b = col_off[r], n = col_off[r + 1] - b, ali = c - b;
   const uint8_t* rf = refb + b;
   uint8_t* rd = readb + b;
-  for (int64_t ali = 0; ali < n; ++ali) {
-    if (rf[ali] == 'C' && rd[ali] == 'C') {
-      if (ali + 1 < n && rd[ali + 1] == '-' && rf[ali + 1] == 'G') {
-        int64_t add = 2;
-        while (ali + add < n && rd[ali + add] == '-' && rf[ali + add] == 'G') ++add;
-        if (ali + add < n && rd[ali + add] == 'G' && rf[ali + add] == 'G') {
-          const uint8_t t = rd[ali + 1]; rd[ali + 1] = rd[ali + add]; rd[ali + add] = t;
-        }
+  if (t1) {
+    if (ali + 1 < n && rd[ali + 1] == '-' && rf[ali + 1] == 'G') {
+      int64_t add = 2;
+      while (ali + add < n && rd[ali + add] == '-' && rf[ali + add] == 'G') ++add;
+      if (ali + add < n && rd[ali + add] == 'G' && rf[ali + add] == 'G') {
+        const uint8_t t = rd[ali + 1]; rd[ali + 1] = rd[ali + add]; rd[ali + add] = t;
       }
     }
-    if (rf[ali] == 'G' && rd[ali] == 'G') {
-      if (ali - 1 > -1 && rd[ali - 1] == '-' && rf[ali - 1] == 'C') {
-        int64_t add = 2;
-        while (ali - add > -1 && rd[ali - add] == '-' && rf[ali - add] == 'C') ++add;
-        if (ali - add > -1 && rd[ali - add] == 'C' && rf[ali - add] == 'C') {
-          const uint8_t t = rd[ali - 1]; rd[ali - 1] = rd[ali - add]; rd[ali - add] = t;
-        }
+  } else {
+    if (ali - 1 > -1 && rd[ali - 1] == '-' && rf[ali - 1] == 'C') {
+      int64_t add = 2;
+      while (ali - add > -1 && rd[ali - add] == '-' && rf[ali - add] == 'C') ++add;
+      if (ali - add > -1 && rd[ali - add] == 'C' && rf[ali - add] == 'C') {
+        const uint8_t t = rd[ali - 1]; rd[ali - 1] = rd[ali - add]; rd[ali - add] = t;
       }
     }
   }
@@ -177,12 +183,16 @@ __global__ void k_init_acc(int n, ReadAcc* acc) {
 inline unsigned nb(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
 template <typename T>
-struct Dev {
+struct Dev {                      // stream-ordered scratch (pool allocator: no device-wide synchronisation)
   T* p = nullptr;
-  ~Dev() { cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * std::max<size_t>(n, 1)); }
+  cudaStream_t st = nullptr;
+  ~Dev() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t n, cudaStream_t s = nullptr) {
+    st = s;
+    return cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(T) * std::max<size_t>(n, 1), s);
+  }
   cudaError_t upload(const T* h, size_t n, cudaStream_t s) {
-    cudaError_t e = alloc(n);
+    cudaError_t e = alloc(n, s);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(p, h, sizeof(T) * n, cudaMemcpyHostToDevice, s);
     return e;
   }
@@ -250,8 +260,8 @@ int dm_align_build(dm_ctx* ctx, const dm_sam_batch* sb, int64_t* n_windows_out, 
   DM_CUDA(ctx, d_seq.upload(sb->seq, (size_t)n_seq, s));
   DM_CUDA(ctx, d_clip_l.upload(sb->clip_left, (size_t)n, s));
   DM_CUDA(ctx, d_clip_r.upload(sb->clip_right, (size_t)n, s));
-  DM_CUDA(ctx, d_raw_ref.alloc(n_raw)); DM_CUDA(ctx, d_raw_read.alloc(n_raw)); DM_CUDA(ctx, d_raw_pos.alloc(n_raw));
-  DM_CUDA(ctx, d_acc.alloc(n)); DM_CUDA(ctx, d_col_lo.alloc(n)); DM_CUDA(ctx, d_keep.alloc(n)); DM_CUDA(ctx, d_nwin.alloc(n));
+  DM_CUDA(ctx, d_raw_ref.alloc(n_raw, s)); DM_CUDA(ctx, d_raw_read.alloc(n_raw, s)); DM_CUDA(ctx, d_raw_pos.alloc(n_raw, s));
+  DM_CUDA(ctx, d_acc.alloc(n, s)); DM_CUDA(ctx, d_col_lo.alloc(n, s)); DM_CUDA(ctx, d_keep.alloc(n, s)); DM_CUDA(ctx, d_nwin.alloc(n, s));
   // per-read arrays of the resident batch
   int rc = dm_batch_reserve(ctx, n, n_events, 0, 0);
   if (rc != DM_OK) return rc;
@@ -266,6 +276,7 @@ int dm_align_build(dm_ctx* ctx, const dm_sam_batch* sb, int64_t* n_windows_out, 
     if (sb->ev_base) DM_CUDA(ctx, cudaMemcpyAsync(b.ev_base, sb->ev_base, (size_t)n_events, H2D, s));
   }
   b.has_ev_base = sb->ev_base != nullptr;
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
   k_init_acc<<<nb(n, 256), 256, 0, s>>>(n, d_acc.p);
   if (n_raw > 0)
     k_expand<<<nb(n_raw, 256), 256, 0, s>>>(n_raw, n_ops, n, d_op_col.p, d_op_off.p, d_op_code.p, d_op_read.p, d_op_ref.p,
@@ -291,11 +302,14 @@ int dm_align_build(dm_ctx* ctx, const dm_sam_batch* sb, int64_t* n_windows_out, 
     k_emit_columns<<<nb(n_cols, 256), 256, 0, s>>>(n_cols, n, b.col_off, d_op_off.p, d_op_col.p, d_col_lo.p, b.strand,
                                                    d_raw_ref.p, d_raw_read.p, d_raw_pos.p, b.col_refbase, b.col_readbase,
                                                    b.col_refpos);
-    k_gap_swap<<<nb(n, 64), 64, 0, s>>>(n, b.col_off, b.col_refbase, b.col_readbase);
+    k_gap_swap<<<nb(n_cols, 256), 256, 0, s>>>(n_cols, n, b.col_off, b.col_refbase, b.col_readbase);
     ctx->launches += 2;
   }
   DM_CUDA(ctx, cudaGetLastError());
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev3, s));
   DM_CUDA(ctx, cudaStreamSynchronize(s));      // host vectors above are pageable
+  DM_CUDA(ctx, cudaEventElapsedTime(&ctx->total_ms, ctx->ev0, ctx->ev3));   // walk kernels + the one size round trip
+  ctx->lstm_ms = 0.f;
   b.n_events = n_events; b.n_cols = n_cols; b.n_windows = n_windows; b.n_frows = n_frows;
   b.from_alignment = true;
   if (n_windows_out) *n_windows_out = n_windows;

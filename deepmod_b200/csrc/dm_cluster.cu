@@ -210,10 +210,14 @@ int ensure_motif(dm_ctx* ctx) {
 }
 
 template <typename T>
-struct DevBuf {
+struct DevBuf {                   // stream-ordered scratch (pool allocator: no device-wide synchronisation)
   T* p = nullptr;
-  ~DevBuf() { cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * std::max<size_t>(n, 1)); }
+  cudaStream_t st = nullptr;
+  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+  cudaError_t alloc(size_t n, cudaStream_t s) {
+    st = s;
+    return cudaMallocAsync(reinterpret_cast<void**>(&p), sizeof(T) * std::max<size_t>(n, 1), s);
+  }
 };
 
 }  // namespace
@@ -238,9 +242,10 @@ int dm_cluster_run(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* cw, in
   DevBuf<int32_t> cov_d, mod_d, pct_d;
   DevBuf<float> prob_d, feat_d, lut_d;
   DevBuf<ClusterW> w_d;
-  DM_CUDA(ctx, flag.alloc(n));
-  DM_CUDA(ctx, block_cnt.alloc(n_blocks));
-  DM_CUDA(ctx, block_off.alloc(n_blocks + 1));
+  DM_CUDA(ctx, flag.alloc(n, s));
+  DM_CUDA(ctx, block_cnt.alloc(n_blocks, s));
+  DM_CUDA(ctx, block_off.alloc(n_blocks + 1, s));
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev0, s));
   k_site_flags<<<n_blocks, 256, 0, s>>>(cells, motif, n, drop_unmodified, flag.p, block_cnt.p);
   k_scan_counts<<<1, 1024, 0, s>>>(block_cnt.p, n_blocks, block_off.p, block_off.p + n_blocks);
   ctx->launches += 2;
@@ -260,20 +265,24 @@ int dm_cluster_run(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* cw, in
   memcpy(hw.w1, cw->w1, sizeof(hw.w1)); memcpy(hw.b1, cw->b1, sizeof(hw.b1));
   memcpy(hw.w2, cw->w2, sizeof(hw.w2)); memcpy(hw.b2, cw->b2, sizeof(hw.b2));
   memcpy(hw.wo, cw->wo, sizeof(hw.wo)); hw.bo = cw->bo[0];
-  DM_CUDA(ctx, lut_d.alloc(lut.size()));
-  DM_CUDA(ctx, w_d.alloc(1));
+  DM_CUDA(ctx, lut_d.alloc(lut.size(), s));
+  DM_CUDA(ctx, w_d.alloc(1, s));
   DM_CUDA(ctx, cudaMemcpyAsync(lut_d.p, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   DM_CUDA(ctx, cudaMemcpyAsync(w_d.p, &hw, sizeof(hw), cudaMemcpyHostToDevice, s));
-  DM_CUDA(ctx, site_idx.alloc(total)); DM_CUDA(ctx, pos_d.alloc(total)); DM_CUDA(ctx, strand_d.alloc(total));
-  DM_CUDA(ctx, cov_d.alloc(total)); DM_CUDA(ctx, mod_d.alloc(total)); DM_CUDA(ctx, pct_d.alloc(total));
-  DM_CUDA(ctx, prob_d.alloc(total));
-  if (want_feat) DM_CUDA(ctx, feat_d.alloc((size_t)total * NF));
+  DM_CUDA(ctx, site_idx.alloc(total, s)); DM_CUDA(ctx, pos_d.alloc(total, s)); DM_CUDA(ctx, strand_d.alloc(total, s));
+  DM_CUDA(ctx, cov_d.alloc(total, s)); DM_CUDA(ctx, mod_d.alloc(total, s)); DM_CUDA(ctx, pct_d.alloc(total, s));
+  DM_CUDA(ctx, prob_d.alloc(total, s));
+  if (want_feat) DM_CUDA(ctx, feat_d.alloc((size_t)total * NF, s));
   k_emit_sites<<<n_blocks, 256, 0, s>>>(flag.p, n, block_off.p, site_idx.p);
   k_cluster_sites<<<nblk(total, 128), 128, 0, s>>>(cells, flag.p, len, site_idx.p, total, w_d.p, lut_d.p, pos_d.p,
                                                    strand_d.p, cov_d.p, mod_d.p, want_feat ? feat_d.p : nullptr,
                                                    prob_d.p, pct_d.p);
   ctx->launches += 2;
   DM_CUDA(ctx, cudaGetLastError());
+  DM_CUDA(ctx, cudaEventRecord(ctx->ev3, s));
+  DM_CUDA(ctx, cudaEventSynchronize(ctx->ev3));
+  DM_CUDA(ctx, cudaEventElapsedTime(&ctx->total_ms, ctx->ev0, ctx->ev3));   // flags + compaction + features + MLP
+  ctx->lstm_ms = 0.f;
   out.pos.resize(total); out.strand.resize(total); out.cov.resize(total); out.mod.resize(total);
   out.pct.resize(total); out.prob.resize(total);
   const auto D2H = cudaMemcpyDeviceToHost;
@@ -301,7 +310,7 @@ int dm_cluster_sites_upload(dm_ctx* ctx, int32_t contig, int64_t n, const int64_
   if (n > 0) {
     DevBuf<int64_t> p;
     DevBuf<int8_t> st;
-    DM_CUDA(ctx, p.alloc(n)); DM_CUDA(ctx, st.alloc(n));
+    DM_CUDA(ctx, p.alloc(n, ctx->stream)); DM_CUDA(ctx, st.alloc(n, ctx->stream));
     DM_CUDA(ctx, cudaMemcpyAsync(p.p, pos, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     DM_CUDA(ctx, cudaMemcpyAsync(st.p, strand, n, cudaMemcpyHostToDevice, ctx->stream));
     k_set_sites<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, p.p, st.p, len, blk);
@@ -323,7 +332,7 @@ int dm_hist_load_rows(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t n, con
   unsigned long long* blk = ctx->cells + 2 * ctx->contig_off[contig] + (strand >= 0 ? 0 : len);
   DevBuf<int64_t> p;
   DevBuf<int32_t> c, m;
-  DM_CUDA(ctx, p.alloc(n)); DM_CUDA(ctx, c.alloc(n)); DM_CUDA(ctx, m.alloc(n));
+  DM_CUDA(ctx, p.alloc(n, ctx->stream)); DM_CUDA(ctx, c.alloc(n, ctx->stream)); DM_CUDA(ctx, m.alloc(n, ctx->stream));
   DM_CUDA(ctx, cudaMemcpyAsync(p.p, pos, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
   DM_CUDA(ctx, cudaMemcpyAsync(c.p, cov, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
   DM_CUDA(ctx, cudaMemcpyAsync(m.p, mod, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
