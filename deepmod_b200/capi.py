@@ -68,6 +68,7 @@ SIGNATURES = {
     "dm_hist_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _i64p]),
     "dm_hist_nonzero": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _i64p, _i32p, _i32p, _i64p]),
     "dm_write_bed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_char_p, C.c_char_p, _i64p]),
+    "dm_event_stats": (C.c_int, [C.c_void_p, C.c_int32, _i64p, C.POINTER(C.c_int16), _i64p, _i64p, _i64p, _fp, _fp]),
     "dm_set_contig_sequence": (C.c_int, [C.c_void_p, C.c_int32, _u8p, C.c_int64]),
     "dm_align_upload": (C.c_int, [C.c_void_p, C.POINTER(DmSamBatch), _i64p, _i64p]),
     "dm_fetch_alignment": (C.c_int, [C.c_void_p, _i64p, _u8p, _u8p, _i64p, _i32p, _i32p]),
@@ -352,6 +353,18 @@ class Context(object):
         self._check(self.lib.dm_detect_batch(self._h, C.byref(pb.struct), _ptr(p1, C.c_float), _ptr(pred, C.c_uint8),
                                              _ptr(status, C.c_int32)), "dm_detect_batch")
         return p1, pred, status
+
+    # -- event-table front-end ------------------------------------------------------------------
+    def event_stats(self, raw_off, raw, ev_off, ev_start, ev_length):
+        """mnormalized + per-event mean/stdv (myDetect.py:266-282, :334-343) -> (mean f32, stdv f32)."""
+        raw_off, ev_off = _arr(raw_off, np.int64), _arr(ev_off, np.int64)
+        raw, ev_start, ev_length = _arr(raw, np.int16), _arr(ev_start, np.int64), _arr(ev_length, np.int64)
+        n_ev = int(ev_off[-1]) if len(ev_off) else 0
+        mean, stdv = np.zeros(n_ev, np.float32), np.zeros(n_ev, np.float32)
+        self._check(self.lib.dm_event_stats(self._h, len(raw_off) - 1, _ptr(raw_off, C.c_int64), _ptr(raw, C.c_int16),
+                                            _ptr(ev_off, C.c_int64), _ptr(ev_start, C.c_int64), _ptr(ev_length, C.c_int64),
+                                            _ptr(mean, C.c_float), _ptr(stdv, C.c_float)), "dm_event_stats")
+        return mean, stdv
 
     # -- from SAM records ------------------------------------------------------------------------
     def set_contig_sequence(self, contig, seq):

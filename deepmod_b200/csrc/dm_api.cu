@@ -260,6 +260,15 @@ int dm_batch_reserve(dm_ctx* ctx, int64_t n, int64_t n_events, int64_t n_cols, i
 
 extern "C" {
 
+int dm_event_stats(dm_ctx* ctx, int32_t n_reads, const int64_t* raw_off, const int16_t* raw, const int64_t* ev_off,
+                   const int64_t* ev_start, const int64_t* ev_length, float* mean_out, float* stdv_out) {
+  if (!ctx || n_reads < 0) return DM_ERR_ARG;
+  if (n_reads > 0 && (!raw_off || !raw || !ev_off || !ev_start || !ev_length || !mean_out || !stdv_out))
+    return fail(ctx, DM_ERR_ARG, "dm_event_stats: null array");
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  return dm_signal_event_stats(ctx, n_reads, raw_off, raw, ev_off, ev_start, ev_length, mean_out, stdv_out);
+}
+
 int dm_set_contig_sequence(dm_ctx* ctx, int32_t contig, const uint8_t* seq, int64_t len) {
   if (!ctx || !seq || len < 0) return DM_ERR_ARG;
   DM_CUDA(ctx, cudaSetDevice(ctx->device));

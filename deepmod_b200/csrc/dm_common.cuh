@@ -125,6 +125,8 @@ void dm_set_error(dm_ctx* ctx, const std::string& msg);
 int dm_batch_reserve(dm_ctx* ctx, int64_t n_reads, int64_t n_events, int64_t n_cols, int64_t n_windows);  // dm_api.cu
 int dm_genome_sequence_upload(dm_ctx* ctx, int32_t contig, const uint8_t* seq, int64_t len);               // dm_align.cu
 int dm_align_build(dm_ctx* ctx, const dm_sam_batch* sb, int64_t* n_windows_out, int64_t* n_cols_out);      // dm_align.cu
+int dm_signal_event_stats(dm_ctx* ctx, int32_t n_reads, const int64_t* raw_off, const int16_t* raw, const int64_t* ev_off,
+                          const int64_t* ev_start, const int64_t* ev_length, float* mean_out, float* stdv_out);   // dm_signal.cu
 int dm_launch_prepare(dm_ctx* ctx);                       // dm_features.cu
 int dm_launch_build_windows(dm_ctx* ctx, float* out_d);   // dm_features.cu
 int dm_launch_accumulate(dm_ctx* ctx);                    // dm_hist.cu

@@ -285,3 +285,31 @@ def make_sam_reads(genome, contig_names, n_reads, seed=5, mean_len=800, len_lo=8
             recs.append("\t".join([q, "4", "*", "0", "0", "*", "*", "0", "0", seq.tobytes().decode(), "*"]))
         lines.extend(recs)
     return lines, reads
+
+
+def make_raw_signals(n_reads, seed=21, mean_events=1500, spikes=True):
+    """Synthetic raw nanopore reads for the event-table front-end: int16 samples, piecewise-constant levels plus noise,
+    some samples before / after the event span and a few spikes.  -> (raw_off, raw, ev_off, ev_start, ev_length)"""
+    rng = np.random.default_rng(seed)
+    raws, starts, lens = [], [], []
+    raw_off, ev_off = [0], [0]
+    for r in range(n_reads):
+        n_ev = int(max(60, rng.gamma(2.0, mean_events / 2.0)))
+        length = (1 + rng.geometric(0.12, n_ev)).astype(np.int64)
+        if r % 3 == 0:
+            length[rng.integers(0, n_ev, 3)] += rng.integers(130, 700, 3)        # long stalls: the >128-sample summation path
+        lead, trail = int(rng.integers(0, 300)), int(rng.integers(0, 300))
+        start = lead + np.concatenate([[0], np.cumsum(length[:-1])])
+        n = int(start[-1] + length[-1]) + trail
+        levels = np.repeat(rng.normal(500 + 40 * (r % 5), 90, n_ev), length)
+        raw = np.empty(n, np.float64)
+        raw[:lead] = rng.normal(520, 120, lead)
+        raw[lead:lead + len(levels)] = levels + rng.normal(0, 12, len(levels))
+        raw[lead + len(levels):] = rng.normal(480, 150, trail)
+        if spikes:
+            raw[rng.integers(0, n, 12)] = rng.integers(-800, 4000, 12)
+        raws.append(np.clip(np.round(raw), -32768, 32767).astype(np.int16))
+        starts.append(start.astype(np.int64)); lens.append(length)
+        raw_off.append(raw_off[-1] + n); ev_off.append(ev_off[-1] + n_ev)
+    return (np.array(raw_off, np.int64), np.concatenate(raws), np.array(ev_off, np.int64), np.concatenate(starts),
+            np.concatenate(lens))

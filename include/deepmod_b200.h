@@ -161,6 +161,13 @@ int dm_write_cluster_bed(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* 
 int dm_detect_batch(dm_ctx* ctx, const dm_batch* b, float* p1_out, uint8_t* pred_out,
                     int32_t* status_out);
 
+/* ---- event-table front-end: raw signal -> per-event statistics ----------------------------------------- */
+/* mnormalized (myDetect.py:266-282) + the per-event mean / stdv loop of getFast5Info (:334-343) for a batch of
+ * reads: raw int16 samples (raw_off per read), events as (start, length) in samples relative to the read's raw
+ * array.  mean_out / stdv_out [ev_off[n_reads]] receive what the reference stores in the '<f4' fields. */
+int dm_event_stats(dm_ctx* ctx, int32_t n_reads, const int64_t* raw_off, const int16_t* raw, const int64_t* ev_off,
+                   const int64_t* ev_start, const int64_t* ev_length, float* mean_out, float* stdv_out);
+
 /* ---- from alignment records (SAM) instead of ready-made columns ---------------------------------------- */
 /* Reference sequence of a contig (upper-case ASCII, length = the contig length given to dm_set_genome); what
  * getRefSeq fetches with `samtools faidx` (myDetect.py:470-483). */
