@@ -32,20 +32,6 @@ int fail(dm_ctx* ctx, int code, const std::string& msg) {
   return code;
 }
 
-uint16_t bf16_bits(float f) {   // round-to-nearest-even, what __float2bfloat16 does
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
-  u += 0x7fffu + ((u >> 16) & 1u);
-  return (uint16_t)(u >> 16);
-}
-float bf16_val(uint16_t b) {
-  uint32_t u = (uint32_t)b << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
-
 // ---- weight images ------------------------------------------------------------------
 // fp32 image: see dm_common.cuh (column permutation n' = j*100 + ug*4 + gate).
 void pack_fp32(const float* kernel, const float* bias, int layer, std::vector<float>& W,

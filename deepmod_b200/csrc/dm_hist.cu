@@ -24,8 +24,7 @@ __global__ void k_accumulate(int n_reads, int64_t n_cols, const int64_t* __restr
                              const uint8_t* __restrict__ readbase, const int64_t* __restrict__ refpos,
                              const int32_t* __restrict__ contig, const int8_t* __restrict__ strand,
                              const int32_t* __restrict__ status, const int64_t* __restrict__ win_off,
-                             const uint8_t* __restrict__ pred, const int64_t* __restrict__ contig_off,
-                             const int64_t* __restrict__ contig_len_cum, int n_contigs,
+                             const uint8_t* __restrict__ pred, const int64_t* __restrict__ contig_off, int n_contigs,
                              unsigned long long* __restrict__ cells, uint8_t base) {
   int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_cols) return;
@@ -150,7 +149,7 @@ int dm_launch_accumulate(dm_ctx* ctx) {
   unsigned blocks = (unsigned)((b.n_cols + 255) / 256);
   k_accumulate<<<blocks, 256, 0, ctx->stream>>>(
       b.n_reads, b.n_cols, b.col_off, b.col_rank, b.col_refbase, b.col_readbase, b.col_refpos,
-      b.contig, b.strand, b.status, b.win_off, b.pred, ctx->contig_off_d, nullptr, ctx->n_contigs,
+      b.contig, b.strand, b.status, b.win_off, b.pred, ctx->contig_off_d, ctx->n_contigs,
       ctx->cells, (uint8_t)ctx->base);
   ctx->launches += 1;
   DM_CUDA(ctx, cudaGetLastError());

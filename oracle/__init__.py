@@ -18,6 +18,11 @@ path, and its arithmetic lives in TensorFlow 1.x
 * the frozen GraphDefs under ``train_deepmod/rnn_*/*.meta`` for the op order of
   the BiLSTM restatement (``tests/test_oracle_graph.py``).
 
+Modules: ``detect_ref`` / ``bilstm`` / ``tf_bundle`` (the core path), ``align_ref`` (SAM/CIGAR walk, pinned by
+running the unmodified ``handle_line`` + ``handle_record``), ``cluster_ref`` (CpG-cluster second pass, pinned by
+running the unmodified ``hm_cluster_predict.py`` / ``sum_chr_mod.py``), ``signal_ref`` (raw-signal normalisation,
+pinned by the unmodified ``mnormalized``), ``cells`` (model of the packed accumulator), ``ref_harness``.
+
 The TensorFlow arithmetic itself (Eigen GEMM summation order, Eigen's float
 sigmoid/tanh) cannot be executed here: **TF-level parity is unpinned**; the
 restatement follows the graph op-for-op in fp64/fp32.
