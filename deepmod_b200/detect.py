@@ -122,12 +122,22 @@ def detect_handler(moptions, ctx, read_files, contig_names, failed):
 
 
 def find_sam_files(wrk_base, recursive=1):
-    """<name>.sam files that have a <name>.events.npz next to them."""
+    """<name>.sam files that have a <name>.events.npz (event tables) or <name>.raw.npz (raw signals) next to them."""
     files = glob.glob(os.path.join(wrk_base, "*.sam"))
     if recursive == 1:
         for depth in ("*", "*/*", "*/*/*"):
             files.extend(glob.glob(os.path.join(wrk_base, depth, "*.sam")))
-    return sorted(f for f in files if os.path.isfile(f[:-4] + ".events.npz"))
+    return sorted(f for f in files if os.path.isfile(f[:-4] + ".events.npz") or os.path.isfile(f[:-4] + ".raw.npz"))
+
+
+def events_from_raw(ctx, path):
+    """Event tables from raw signals on the GPU: mnormalized + per-event mean/stdv (myDetect.py:266-282, :334-343)."""
+    z = reads_io.load_raw(path)
+    mean, stdv = ctx.event_stats(z["raw_off"], z["raw"], z["ev_off"], z["ev_start"], z["ev_length"])
+    off = z["ev_off"]
+    length = z["ev_length"].astype(np.float32)
+    return {str(q): dict(ev_mean=mean[off[i]:off[i + 1]], ev_stdv=stdv[off[i]:off[i + 1]], ev_len=length[off[i]:off[i + 1]],
+                         ev_base=z["ev_base"][off[i]:off[i + 1]]) for i, q in enumerate(z["qnames"])}
 
 
 def detect_handler_sam(moptions, ctx, sam_files, contig_names, failed):
@@ -135,7 +145,10 @@ def detect_handler_sam(moptions, ctx, sam_files, contig_names, failed):
     world, rank, _ = _dist_env()
     n_reads = n_windows = 0
     for path in sam_files:
-        reads = reads_io.load_events(path[:-4] + ".events.npz")
+        if os.path.isfile(path[:-4] + ".events.npz"):
+            reads = reads_io.load_events(path[:-4] + ".events.npz")
+        else:
+            reads = events_from_raw(ctx, path[:-4] + ".raw.npz")
         with open(path) as fh:
             lines = fh.read().splitlines()
         arrays, qnames, skipped = sam.tokenise(lines, reads, contig_names, moptions)

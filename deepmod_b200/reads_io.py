@@ -74,3 +74,19 @@ def read_fasta(path):
     if names:
         seqs.append(np.frombuffer("".join(cur).upper().encode(), np.uint8))
     return names, seqs
+
+
+def save_raw(path, qnames, raw_off, raw, ev_off, ev_start, ev_length, ev_base):
+    """<name>.raw.npz: raw int16 signals + event boundaries + called bases (what FAST5 reading + getEvent provide,
+    myDetect.py:133-261, before normalisation)."""
+    if not path.endswith(".raw.npz"):
+        raise ValueError("raw signal batches are named *.raw.npz")
+    with open(path, "wb") as fh:
+        np.savez(fh, qnames=np.array(list(qnames)), raw_off=np.asarray(raw_off, np.int64), raw=np.asarray(raw, np.int16),
+                 ev_off=np.asarray(ev_off, np.int64), ev_start=np.asarray(ev_start, np.int64),
+                 ev_length=np.asarray(ev_length, np.int64), ev_base=np.asarray(ev_base, np.uint8))
+
+
+def load_raw(path):
+    with np.load(path, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}

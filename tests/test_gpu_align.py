@@ -134,3 +134,56 @@ def test_detect_cli_from_sam_files(samset, tmp_path):
                 got[n + s] = open(p).read()
     assert got == want and len(got) == 4
     assert os.path.isfile(os.path.join(out, "s1.done"))
+
+
+def test_detect_cli_from_raw_signals(samset, tmp_path):
+    """raw int16 signals -> (GPU) event statistics -> (GPU) CIGAR walk -> BiLSTM -> BED, one `detect` call; equals the
+    run that is handed the oracle's event tables."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from deepmod_b200 import checkpoint, reads_io, synth
+    from oracle import signal_ref
+    genome, names, lines, reads = samset
+    rng = np.random.default_rng(3)
+    qn = list(reads)
+    raw_off, ev_off, raws, starts, lens, bases = [0], [0], [], [], [], []
+    ev_reads = {}
+    for q in qn:
+        n_ev = len(reads[q]["ev_mean"])
+        length = (1 + rng.geometric(0.15, n_ev)).astype(np.int64)
+        lead = int(rng.integers(0, 50))
+        start = lead + np.concatenate([[0], np.cumsum(length[:-1])])
+        n = int(start[-1] + length[-1]) + 20
+        lv = np.repeat(rng.normal(500, 90, n_ev), length)
+        raw = np.concatenate([rng.normal(500, 100, lead), lv + rng.normal(0, 10, len(lv)), rng.normal(500, 100, 20)])
+        raw = np.round(raw).astype(np.int16)
+        sig = signal_ref.normalize(raw, start, length)
+        m, s = signal_ref.event_stats(sig, start, length)
+        ev_reads[q] = dict(ev_mean=m, ev_stdv=s, ev_len=length.astype(np.float32), ev_base=reads[q]["ev_base"])
+        raws.append(raw); starts.append(start); lens.append(length); bases.append(reads[q]["ev_base"])
+        raw_off.append(raw_off[-1] + n); ev_off.append(ev_off[-1] + n_ev)
+    with open(tmp_path / "ref.fa", "w") as fh:
+        for n_, g in zip(names, genome):
+            fh.write(">%s\n%s\n" % (n_, g.tobytes().decode()))
+    mod = str(tmp_path / "m.npz")
+    checkpoint.save_npz(checkpoint.Model.from_dict(golden_model("conmodC_P100")), mod)
+    outs = {}
+    for kind in ("raw", "events"):
+        wrk = tmp_path / kind
+        wrk.mkdir()
+        open(wrk / "b.sam", "w").write("\n".join(lines) + "\n")
+        if kind == "raw":
+            reads_io.save_raw(str(wrk / "b.raw.npz"), qn, raw_off, np.concatenate(raws), ev_off, np.concatenate(starts),
+                              np.concatenate(lens), np.concatenate(bases))
+        else:
+            reads_io.save_events(str(wrk / "b.events.npz"), ev_reads)
+        out = str(tmp_path / ("out_" + kind))
+        r = subprocess.run([sys.executable, "-m", "deepmod_b200", "detect", "--wrkBase", str(wrk), "--Ref", str(tmp_path / "ref.fa"),
+                            "--modfile", mod, "--Base", "C", "--FileID", "r", "--outFolder", out], capture_output=True, text=True,
+                           timeout=600, cwd=ROOT)
+        assert r.returncode == 0, r.stdout + r.stderr
+        d = os.path.join(out, "r")
+        outs[kind] = {f: open(os.path.join(d, f)).read() for f in sorted(os.listdir(d))}
+    assert outs["raw"] == outs["events"] and len(outs["raw"]) == 4
