@@ -334,6 +334,14 @@ def main():
                 "kernel": "k_lstm_fp32", "kernel_ms": lstm_avg, "peak_source": "nominal fp32 FFMA (SIMT parity path)",
                 "flop_per_base": FLOP_PER_BASE}
 
+    if args.precision == "bf16":
+        # the pipe that actually binds k_lstm_tc: 5 MUFU.TANH per unit and cell-step (4 at t = 0) = 32 400 per base,
+        # 16 per clock and SM (tools/micro/mufu_bench.cu measures 16.5 lanes/clk/SM on this part)
+        mhz = (clocks or {}).get("sm_mhz") or float(pk.get("sm_max_mhz", 1965.0))
+        mufu_peak = 16.0 * 148 * mhz * 1e6
+        mufu_ach = n_ok * 32400.0 / (lstm_avg * 1e-3)
+        roof["mufu"] = {"achieved": mufu_ach / 1e12, "peak": mufu_peak / 1e12, "unit": "Tops/s", "frac": mufu_ach / mufu_peak,
+                        "note": "MUFU.TANH issue rate at the SM clock sampled under load"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic reads (SURVEY 8(d) generator); trained rnn_conmodC_P100wd21_f7ne1u0_4 weights",
