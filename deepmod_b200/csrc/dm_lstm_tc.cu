@@ -207,7 +207,7 @@ __device__ __forceinline__ int tau_row(int dir, int tau) { return dir == 0 ? tau
 // drained relay (peer CTA); 22 TMEM allocator / hidden-state-written relay (peer); 23 stage-landed
 // relay (peer).  The relays exist because a cluster-scope release-arrive costs ~1000 cycles: the
 // peer's 20 epilogue warps arrive on cheap CTA-local barriers and ONE thread forwards each phase.
-template <bool PAIR>
+template <bool PAIR, bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__ win_frow, dm_dev_weights w,
           float* __restrict__ p1_out, uint8_t* __restrict__ pred_out, int n_tiles, int max_steps,
@@ -216,13 +216,14 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + OFF_BAR;
   using G = Geo<PAIR>;
-  // development switches ride in the upper bits of max_steps (see dm_debug_tc_windows):
+  // DBG instantiation only (dm_debug_tc_windows): development switches ride in the upper bits of max_steps
   //   0x100 epilogue skips the gate math, 0x200 no tcgen05.mma is issued, 0x400 no weight loads
-  const bool dbg_nomath = (max_steps & 0x100) != 0, dbg_nomma = (max_steps & 0x200) != 0, dbg_noload = (max_steps & 0x400) != 0;
-  max_steps &= 0xFF;
-  // optional timeline of CTA 0 behind the operand dump: [role][step][slot] SM clocks
-  unsigned long long* ts = (dbg != nullptr && blockIdx.x == 0) ? reinterpret_cast<unsigned long long*>(dbg + OFF_W) : nullptr;
-#define TS(idx) do { if (ts) ts[(idx)] = clock64(); } while (0)
+  // and a timeline of CTA 0 is written behind the operand dump: [role][step][slot] SM clocks.
+  const bool dbg_nomath = DBG && (max_steps & 0x100) != 0, dbg_nomma = DBG && (max_steps & 0x200) != 0,
+             dbg_noload = DBG && (max_steps & 0x400) != 0;
+  max_steps = DBG ? (max_steps & 0xFF) : 2 * TC_STEPS_PER_DIR;
+  unsigned long long* ts = (DBG && dbg != nullptr && blockIdx.x == 0) ? reinterpret_cast<unsigned long long*>(dbg + OFF_W) : nullptr;
+#define TS(idx) do { if (DBG && ts) ts[(idx)] = clock64(); } while (0)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t crank = PAIR ? cluster_rank() : 0u;      // 0 = leader (issues the MMAs of the pair)
   const bool leader = crank == 0;
@@ -560,7 +561,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
 #undef TS
   tc_fence_before();
   __syncthreads();
-  if (dbg != nullptr && blockIdx.x == 0)
+  if (DBG && dbg != nullptr && blockIdx.x == 0)
     for (int i = tid; i < OFF_W / 16; i += TC_THREADS)
       reinterpret_cast<uint4*>(dbg)[i] = *reinterpret_cast<const uint4*>(smem + i * 16);
   if (PAIR) cluster_sync_all();       // the peer may still be reading this CTA's operands / signalling its barriers
@@ -691,8 +692,10 @@ void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool 
 
 static int tc_prepare(dm_ctx* ctx) {
   if (!ctx->tc_attr_set) {
-    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     DM_CUDA(ctx, cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ctx->tc_attr_set = true;
   }
@@ -705,6 +708,7 @@ static int tc_launch(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* w
   // persistent CTAs: one per SM (an even number, so that pairs stay whole); the debug entry runs one tile per CTA
   unsigned grid = (unsigned)(ctx->sm_count & ~1);
   if (dbg != nullptr || max_steps != 2 * TC_STEPS_PER_DIR || grid > tiles) grid = tiles;
+  const bool debug = dbg != nullptr || max_steps != 2 * TC_STEPS_PER_DIR;
   if (ctx->tc_pair) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -718,9 +722,12 @@ static int tc_launch(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* w
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstm_tc<true>, feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg));
+    if (debug) DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstm_tc<true, true>, feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg));
+    else DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstm_tc<true, false>, feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg));
+  } else if (debug) {
+    k_lstm_tc<false, true><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg);
   } else {
-    k_lstm_tc<false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg);
+    k_lstm_tc<false, false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg);
   }
   ctx->launches += 1;
   DM_CUDA(ctx, cudaGetLastError());
