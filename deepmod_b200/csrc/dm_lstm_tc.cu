@@ -466,9 +466,8 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             if (stamp) TS(ts0 + g * 16 + 3 * j + 1);
             uint32_t v[16];
             tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
-            tc_wait_ld();
+            tc_wait_ld();          // .sync.aligned: the whole warp's loads have landed here, no __syncwarp needed
             tc_fence_before();
-            __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_TEMPTY + tslot));      // CTA-local; the peer's relay forwards
             if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
             if (stamp) TS(ts0 + g * 16 + 3 * j + 2);
