@@ -89,6 +89,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n\t}"
       ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
+// non-blocking probe: has the phase with this parity completed?
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -265,18 +275,25 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   // direction init: zero the hidden tiles, stage x(0), x(1) and the step-0 extras of h0[1]
   auto dir_init = [&](int dir) {
     const int et = tid;
-    uint4 z = make_uint4(0, 0, 0, 0);
+    // the global loads go first so that their latency hides behind the zeroing and the barrier
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (et < 256)
+      v = *reinterpret_cast<const uint4*>(feat_tc + ((int64_t)s_frow[et & 127] + tau_row(dir, et >> 7)) * 16);
+    else if (et < 384) {
+      const uint2 e = *reinterpret_cast<const uint2*>(feat_tc + ((int64_t)s_frow[et - 256] + tau_row(dir, 0)) * 16 + 8);
+      v.x = e.x; v.y = e.y;
+    }
+    const uint4 z = make_uint4(0, 0, 0, 0);
     for (int i = et; i < (5 * TC_HTILE) / 16; i += TC_EPI_THREADS)
       *reinterpret_cast<uint4*>(smem + OFF_H0 + i * 16) = z;
     epi_bar();
     if (et < 256) {
       const int r = et & 127, tau = et >> 7;
-      const uint4 v = *reinterpret_cast<const uint4*>(feat_tc + ((int64_t)s_frow[r] + tau_row(dir, tau)) * 16);
       *reinterpret_cast<uint4*>(smem + OFF_X + tau * TC_ACOL + (r >> 3) * 128 + (r & 7) * 16) = v;
     } else if (et < 384) {
       const int r = et - 256;
-      const uint2 v = *reinterpret_cast<const uint2*>(feat_tc + ((int64_t)s_frow[r] + tau_row(dir, 0)) * 16 + 8);
-      *reinterpret_cast<uint2*>(smem + OFF_H0 + TC_HTILE + 12 * TC_ACOL + (r >> 3) * 128 + (r & 7) * 16 + 8) = v;
+      *reinterpret_cast<uint2*>(smem + OFF_H0 + TC_HTILE + 12 * TC_ACOL + (r >> 3) * 128 + (r & 7) * 16 + 8) =
+          make_uint2(v.x, v.y);
     }
     fence_async_smem();
     epi_bar();
@@ -458,6 +475,17 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           // h2 is single-buffered and its old value is an operand of ALL five chunks of this very
           // step: layer 2 keeps its new h in registers until the last chunk's MMAs have retired
           uint32_t hkeep[TC_NCHUNK][2];
+          // ... which they normally have by the time this step starts (the issuers run ahead): one probe of the last
+          // chunk's barrier decides whether the stores can go out chunk by chunk like in the other layers
+          bool direct = true;
+          if (l == 2) {
+            // (chunks 3 and 4 are the last ones of the two issuer threads, whose MMAs retire in order per thread)
+            uint32_t s3 = tslot + (TC_NCHUNK - 2), u3 = tuse, s4 = tslot + (TC_NCHUNK - 1), u4 = tuse;
+            if (s3 >= TC_TSLOTS) { s3 -= TC_TSLOTS; ++u3; }
+            if (s4 >= TC_TSLOTS) { s4 -= TC_TSLOTS; ++u4; }
+            const bool done = mbar_test(bar0 + 8 * (BAR_TFULL + s3), u3 & 1) && mbar_test(bar0 + 8 * (BAR_TFULL + s4), u4 & 1);
+            direct = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
+          }
 #pragma unroll
           for (int j = 0; j < TC_NCHUNK; ++j) {
             if (stamp) TS(ts0 + g * 16 + 3 * j);
@@ -502,7 +530,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             const int u0 = 20 * j + 4 * sgrp;
             unsigned char* dst = smem + htile + (u0 >> 3) * TC_ACOL + row_off + (u0 & 7) * 2;
             const uint32_t h01 = pack_bf16(hn[0], hn[1]), h23 = pack_bf16(hn[2], hn[3]);
-            if (l == 2) {
+            if (l == 2 && !direct) {
               hkeep[j][0] = h01; hkeep[j][1] = h23;
               if (j == TC_NCHUNK - 1) {
 #pragma unroll
