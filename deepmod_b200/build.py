@@ -37,7 +37,8 @@ def build(force=False, verbose=False, jobs=None):
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        # DM_NVCC_EXTRA: extra flags for tuning sweeps (e.g. -DTC_NLUT=2); not used by the shipped build
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("DM_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:
