@@ -27,32 +27,34 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, jobs=None):
-    """Compile every .cu of the library for sm_100a and link the shared object."""
-    if not force and not stale():
+def build(force=False, verbose=False, jobs=None, out=None, extra=None):
+    """Compile every .cu of the library for sm_100a and link the shared object.
+
+    ``out`` / ``extra``: another output path and extra nvcc flags (tuning variants, see tools/tc_sweep.py)."""
+    if out is None and not force and not stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build") if out is None else out + ".obj"
     os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src[:-3] + ".o")
         # DM_NVCC_EXTRA: extra flags for tuning sweeps (e.g. -DTC_NLUT=2); not used by the shipped build
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("DM_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("DM_NVCC_EXTRA", "").split() + list(extra or []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:
-        out, _ = p.communicate()
-        if verbose and out:
-            sys.stderr.write(out)
+        log, _ = p.communicate()
+        if verbose and log:
+            sys.stderr.write(log)
         if p.returncode != 0:
-            raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, log))
         objs.append(obj)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out or LIB] + objs
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

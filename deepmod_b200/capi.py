@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdeepmod_b200.so")
+# DEEPMOD_B200_LIB: load another build of the library (tuning sweeps); there is still no CPU fallback
+LIB_PATH = os.environ.get("DEEPMOD_B200_LIB") or os.path.join(HERE, "libdeepmod_b200.so")
 
 FP32, BF16, BF16_1CTA = 0, 1, 2
 READ_OK, READ_MISMATCH, READ_BAD_ALIGN, READ_LESS_EVENT, READ_NO_MATCH = 0, 1, 2, 3, 4

@@ -45,6 +45,12 @@ constexpr int TC_HCOLS = 13;            // 100 units + 4 extra K slots
 constexpr int TC_HTILE = TC_HCOLS * TC_ACOL;
 constexpr int TC_STEPS_PER_DIR = 33;
 constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand dump
+#ifndef TC_PREFETCH
+#define TC_PREFETCH 0      // 1: the accumulator load of chunk j+1 is issued before the stores of chunk j
+#endif
+#ifndef TC_SKEW
+#define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
+#endif
 
 // Geometry of the weight stream: one stage = the B operand of one N-chunk (all K core columns).
 // PAIR = two CTAs of a cluster drive ONE tcgen05.mma.cta_group::2 (M = 256, 128 windows each): every
@@ -138,6 +144,13 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// same, with the loaded registers as in/out operands: no consumer of v can be scheduled above the wait
+__device__ __forceinline__ void tc_wait_ld16(uint32_t (&v)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :: "memory");
+}
 // ---- CTA-pair (cta_group::2) variants ----
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -153,7 +166,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) 
   asm volatile(
       "{\n\t.reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
       ::"r"(bar), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
@@ -297,6 +310,10 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
     }
     fence_async_smem();
     epi_bar();
+    if (TC_SKEW > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < (long long)sgrp * TC_SKEW) { }
+    }
   };
   if (warp < TC_EPI_WARPS) {
     for (int i = tid; i < 5 * 128; i += TC_EPI_THREADS) s_part[i] = 0.f;
@@ -486,15 +503,22 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             const bool done = mbar_test(bar0 + 8 * (BAR_TFULL + s3), u3 & 1) && mbar_test(bar0 + 8 * (BAR_TFULL + s4), u4 & 1);
             direct = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
           }
+          uint32_t v[16];
+          if (TC_PREFETCH) {
+            mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+            tc_fence_after();
+            tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
+          }
 #pragma unroll
           for (int j = 0; j < TC_NCHUNK; ++j) {
             if (stamp) TS(ts0 + g * 16 + 3 * j);
-            mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
-            tc_fence_after();
-            if (stamp) TS(ts0 + g * 16 + 3 * j + 1);
-            uint32_t v[16];
-            tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
-            tc_wait_ld();          // .sync.aligned: the whole warp's loads have landed here, no __syncwarp needed
+            if (!TC_PREFETCH) {
+              mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+              tc_fence_after();
+              if (stamp) TS(ts0 + g * 16 + 3 * j + 1);
+              tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
+            }
+            tc_wait_ld16(v);       // .sync.aligned: the whole warp's loads have landed here, no __syncwarp needed
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_TEMPTY + tslot));      // CTA-local; the peer's relay forwards
             if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
@@ -521,6 +545,13 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
                 hn[u] = tanh_mufu(cn[k]) * so;
               }
               cst[l][j][p] = __floats2half2_rn(cn[0], cn[1]);
+            }
+            if (TC_PREFETCH && j + 1 < TC_NCHUNK) {
+              // v is dead: the next chunk's barrier probe and TMEM load overlap this chunk's packing and stores
+              // (same cell-step only: its MMAs never depend on what this step's epilogue still has to write)
+              mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+              tc_fence_after();
+              tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
             }
             if (l == 2 && t == 10) {
               const float* cw = s_cls + dir * DM_HIDDEN + 20 * j + 4 * sgrp;
