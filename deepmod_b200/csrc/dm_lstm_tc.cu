@@ -46,7 +46,7 @@ constexpr int TC_HTILE = TC_HCOLS * TC_ACOL;
 constexpr int TC_STEPS_PER_DIR = 33;
 constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand dump
 #ifndef TC_PREFETCH
-#define TC_PREFETCH 0      // 1: the accumulator load of chunk j+1 is issued before the stores of chunk j
+#define TC_PREFETCH 1      // 1: the accumulator load of chunk j+1 is issued before the stores of chunk j
 #endif
 #ifndef TC_SKEW
 #define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
@@ -196,6 +196,16 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint64_t adesc, uint64_
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// one lane of the (converged) warp; the same lane every time for the full mask
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); }
 
@@ -392,24 +402,26 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   } else if ((warp == W_MMA || warp == W_RELAY) && leader) {
     // ================= MMA issuers =================
     // Issuing is single-threaded and latency-bound (two mbarrier waits + 13 tcgen05.mma + two commits per
-    // N-chunk), so TWO threads in different warps take alternate chunks; chunks own disjoint accumulator
-    // slots and weight stages, and each thread's commits cover exactly its own MMAs.
-    if (lane == 0) {
+    // N-chunk), so TWO warps take alternate chunks; chunks own disjoint accumulator slots and weight
+    // stages, and each issuer's commits cover exactly its own MMAs.  The whole warp walks the loop
+    // converged and one elected lane issues: descriptors then live in uniform registers (a loop under
+    // `if (lane == 0)` makes the compiler broadcast every operand of every MMA through a waterfall loop).
+    {
       const uint32_t mine = warp == W_MMA ? 0u : 1u;
       constexpr uint32_t idesc = umma_idesc(PAIR ? 256 : 128, TC_CHUNK_N);
       constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);         // SBO = 128 B, descriptor version 1
       constexpr uint32_t b_step = (2 * G::BCOL) >> 4;                // two K core columns per MMA
       uint32_t slot = 0, use = 0, tslot = 0, tuse = 0, c = 0;
       FOR_EACH_STEP({
-        if (mine == 0) TS(g * 8 + 0);
+        if (mine == 0 && lane == 0) TS(g * 8 + 0);
         // inputs of this cell-step were written by the epilogues of steps <= g-2, or g-1 in the
         // fill/drain corners of the wavefront (and across the direction switch)
         const int G = G0 + g;
-        if (G >= 2) mbar_wait_cluster(bar0 + 8 * (BAR_HDONE + (G & 1)), ((G - 2) >> 1) & 1);
+        if (G >= 2) mbar_wait(bar0 + 8 * (BAR_HDONE + (G & 1)), ((G - 2) >> 1) & 1);
         const bool wait1 = d == 0 || (d == 1 && l == 0) || d == 12;     // d == 0: first step after a (re-)initialisation
-        if (wait1 && G >= 1) mbar_wait_cluster(bar0 + 8 * (BAR_HDONE + ((G - 1) & 1)), ((G - 1) >> 1) & 1);
+        if (wait1 && G >= 1) mbar_wait(bar0 + 8 * (BAR_HDONE + ((G - 1) & 1)), ((G - 1) >> 1) & 1);
         tc_fence_after();
-        if (mine == 0) TS(g * 8 + 1);
+        if (mine == 0 && lane == 0) TS(g * 8 + 1);
         // A operand = ascending chain of core columns [n0 columns at base0 | rest at base1]; one
         // descriptor (low word) per K=16 step, shared by the five N-chunks of the step
         uint32_t base0, base1;
@@ -429,8 +441,8 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
         }
         for (int j = 0; j < TC_NCHUNK; ++j, ++c) {
           if ((c & 1u) == mine) {
-            if (tuse > 0) mbar_wait_cluster(bar0 + 8 * (BAR_TEMPTY + tslot), (tuse - 1) & 1);
-            if (!dbg_noload) mbar_wait_cluster(bar0 + 8 * (BAR_FULL + slot), use & 1);
+            if (tuse > 0) mbar_wait(bar0 + 8 * (BAR_TEMPTY + tslot), (tuse - 1) & 1);
+            if (!dbg_noload) mbar_wait(bar0 + 8 * (BAR_FULL + slot), use & 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + tslot * TC_CHUNK_N;
             const uint32_t b_lo = (((sbase + OFF_W + slot * G::STAGE) >> 4) & 0x3FFFu) | ((uint32_t)(G::BCOL >> 4) << 16);
@@ -440,14 +452,18 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
                 if (i >= nk16) break;
                 const uint64_t ad = ((uint64_t)desc_hi << 32) | a_lo[i];
                 const uint64_t bd = ((uint64_t)desc_hi << 32) | (b_lo + i * b_step);
-                if (PAIR) tc_mma2(d_tmem, ad, bd, idesc, i > 0 ? 1u : 0u);
-                else tc_mma(d_tmem, ad, bd, idesc, i > 0 ? 1u : 0u);
+                if (elect_one()) {
+                  if (PAIR) tc_mma2(d_tmem, ad, bd, idesc, i > 0 ? 1u : 0u);
+                  else tc_mma(d_tmem, ad, bd, idesc, i > 0 ? 1u : 0u);
+                }
               }
             }
             // weight stage reusable / accumulator chunk ready once these MMAs retire (in both CTAs of a pair)
-            if (PAIR) { tc_commit2(bar0 + 8 * (BAR_EMPTY + slot)); tc_commit2(bar0 + 8 * (BAR_TFULL + tslot)); }
-            else      { tc_commit(bar0 + 8 * (BAR_EMPTY + slot));  tc_commit(bar0 + 8 * (BAR_TFULL + tslot)); }
-            if (mine == 0 || j == 1 || j == 3) TS(g * 8 + 2 + j);
+            if (elect_one()) {
+              if (PAIR) { tc_commit2(bar0 + 8 * (BAR_EMPTY + slot)); tc_commit2(bar0 + 8 * (BAR_TFULL + tslot)); }
+              else      { tc_commit(bar0 + 8 * (BAR_EMPTY + slot));  tc_commit(bar0 + 8 * (BAR_TFULL + tslot)); }
+            }
+            if (lane == 0 && (mine == 0 || j == 1 || j == 3)) TS(g * 8 + 2 + j);
           }
           if (++slot == G::NSTAGE) { slot = 0; ++use; }
           if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
