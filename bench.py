@@ -220,6 +220,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--reads", type=int, default=N_READS, help="reads per GPU and step")
+    ap.add_argument("--pipeline", type=int, default=0, help="dm_set_pipeline for the e2e leg (0 = by size, 1 = off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity-leg", action="store_true")
     ap.add_argument("--no-next-rows", action="store_true")
@@ -290,6 +291,7 @@ def main():
     out = {"pred": torch.empty(max(ppb.n_windows, 1), dtype=torch.uint8, pin_memory=True).numpy()[:ppb.n_windows],
            "status": torch.empty(max(ppb.n_reads, 1), dtype=torch.int32, pin_memory=True).numpy()[:ppb.n_reads]}
     ctx.hist_clear()
+    ctx.set_pipeline(args.pipeline)
     for _ in range(2):
         ctx.detect_batch(ppb, want_p1=False, want_pred=True, out=out)
     barrier()

@@ -83,6 +83,7 @@ SIGNATURES = {
     "dm_detect_batch": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _fp, _u8p, _i32p]),
     "dm_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _i64p]),
     "dm_detect_resident": (C.c_int, [C.c_void_p, C.c_int]),
+    "dm_set_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
     "dm_fetch_results": (C.c_int, [C.c_void_p, _fp, _u8p, _i32p]),
     "dm_build_windows": (C.c_int, [C.c_void_p, _fp]),
     "dm_launch_count": (C.c_int64, [C.c_void_p]),
@@ -354,6 +355,10 @@ class Context(object):
         self._check(self.lib.dm_detect_batch(self._h, C.byref(pb.struct), _ptr(p1, C.c_float), _ptr(pred, C.c_uint8),
                                              _ptr(status, C.c_int32)), "dm_detect_batch")
         return p1, pred, status
+
+    def set_pipeline(self, parts):
+        """Sub-batch pipelining of detect_batch: 0 = by batch size, 1 = off, n = always n read ranges."""
+        self._check(self.lib.dm_set_pipeline(self._h, int(parts)), "dm_set_pipeline")
 
     # -- event-table front-end ------------------------------------------------------------------
     def event_stats(self, raw_off, raw, ev_off, ev_start, ev_length):

@@ -158,6 +158,8 @@ void dm_destroy(dm_ctx* ctx) {
     cudaFree(b->win_off); cudaFree(b->col_rank); cudaFree(b->win_col); cudaFree(b->win_frow);
     cudaFree(b->status); cudaFree(b->align_status); cudaFree(b->feat); cudaFree(b->feat_tc); cudaFree(b->p1); cudaFree(b->pred);
   }
+  cudaFree(ctx->scratch2);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   cudaFree(ctx->fw_x);
   cudaFree(ctx->contig_off_d); cudaFree(ctx->cells); cudaFree(ctx->motif); cudaFree(ctx->genome);
   cudaFree(ctx->scratch); cudaFree(ctx->hbuf); cudaFree(ctx->dpart);
@@ -396,8 +398,149 @@ int dm_fetch_results(dm_ctx* ctx, float* p1_out, uint8_t* pred_out, int32_t* sta
   return DM_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+// Puts the second pipeline slot where every launcher looks (ctx->b, ctx->stream, ctx->scratch) for the
+// lifetime of the object.
+struct SlotSwap {
+  dm_ctx* c;
+  bool on;
+  SlotSwap(dm_ctx* ctx, bool second) : c(ctx), on(second) { flip(); }
+  ~SlotSwap() { flip(); }
+  void flip() {
+    if (!on) return;
+    std::swap(c->b, c->b2);
+    std::swap(c->stream, c->stream2);
+    std::swap(c->scratch, c->scratch2);
+    std::swap(c->scratch_bytes, c->scratch2_bytes);
+  }
+};
+
+// dm_detect_batch for a large batch: contiguous read ranges balanced by events, alternating between two
+// slots (device batch + stream + scratch each), so that the host->device copy of part k+1 and the
+// device->host copy of part k-1 run under the kernels of part k.  Parts accumulate into the same
+// per-position cells; results land at their window / read offsets in the caller's arrays.
+int detect_batch_pipelined(dm_ctx* ctx, const dm_batch* hb, int parts, float* p1_out, uint8_t* pred_out,
+                           int32_t* status_out) {
+  const int n = hb->n_reads;
+  if (!hb->ev_off || !hb->col_off || !hb->start_clip || !hb->end_clip || !hb->contig || !hb->strand)
+    return fail(ctx, DM_ERR_ARG, "dm_detect_batch: null per-read array");
+  if (hb->ev_off[0] != 0 || hb->col_off[0] != 0) return fail(ctx, DM_ERR_ARG, "dm_detect_batch: offsets must start at 0");
+  DM_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->stream2) DM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+  const bool accumulate = ctx->cells != nullptr;
+  // read ranges with about the same number of events
+  std::vector<int> cut(1, 0);
+  const int64_t total_ev = hb->ev_off[n];
+  for (int k = 1, r = 0; k < parts; ++k) {
+    const int64_t want = total_ev * k / parts;
+    while (r < n && hb->ev_off[r] < want) ++r;
+    if (r > cut.back() && r < n) cut.push_back(r);
+  }
+  cut.push_back(n);
+  const int np = (int)cut.size() - 1;
+  std::vector<cudaEvent_t> ev((size_t)np * 4, nullptr);
+  struct Finish {          // whatever happens, nothing of this call is still in flight when it returns
+    dm_ctx* c; std::vector<cudaEvent_t>& ev;
+    ~Finish() {
+      cudaStreamSynchronize(c->stream);
+      if (c->stream2) cudaStreamSynchronize(c->stream2);
+      for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e);
+    }
+  } finish{ctx, ev};
+  for (auto& e : ev) DM_CUDA(ctx, cudaEventCreate(&e));
+  int64_t win_base = 0;
+  size_t h2d = 0;
+  struct Part { int r0 = 0, m = 0; int64_t nw = 0, win0 = 0; };
+  std::vector<Part> part((size_t)np);
+  // results of part k go out on its own stream; issued one iteration late so that a blocking copy into
+  // pageable host memory waits with the next part already queued
+  auto fetch = [&](int k) -> int {
+    const Part& pt = part[(size_t)k];
+    SlotSwap slot(ctx, (k & 1) != 0);
+    cudaStream_t s = ctx->stream;
+    const dm_dev_batch& b = ctx->b;
+    const auto D2H = cudaMemcpyDeviceToHost;
+    if (p1_out && pt.nw > 0) DM_CUDA(ctx, cudaMemcpyAsync(p1_out + pt.win0, b.p1, sizeof(float) * pt.nw, D2H, s));
+    if (pred_out && pt.nw > 0) DM_CUDA(ctx, cudaMemcpyAsync(pred_out + pt.win0, b.pred, pt.nw, D2H, s));
+    if (status_out && pt.m > 0) DM_CUDA(ctx, cudaMemcpyAsync(status_out + pt.r0, b.status, sizeof(int32_t) * pt.m, D2H, s));
+    return DM_OK;
+  };
+  for (int k = 0; k < np; ++k) {
+    const int r0 = cut[k], r1 = cut[k + 1], m = r1 - r0;
+    const int64_t e0 = hb->ev_off[r0], c0 = hb->col_off[r0];
+    std::vector<int64_t> ev_off((size_t)m + 1), col_off((size_t)m + 1);
+    for (int r = 0; r <= m; ++r) { ev_off[r] = hb->ev_off[r0 + r] - e0; col_off[r] = hb->col_off[r0 + r] - c0; }
+    dm_batch sub{};
+    sub.n_reads = m;
+    sub.ev_off = ev_off.data(); sub.col_off = col_off.data();
+    sub.ev_mean = hb->ev_mean ? hb->ev_mean + e0 : nullptr;
+    sub.ev_stdv = hb->ev_stdv ? hb->ev_stdv + e0 : nullptr;
+    sub.ev_len = hb->ev_len ? hb->ev_len + e0 : nullptr;
+    sub.ev_base = hb->ev_base ? hb->ev_base + e0 : nullptr;
+    sub.col_refbase = hb->col_refbase ? hb->col_refbase + c0 : nullptr;
+    sub.col_readbase = hb->col_readbase ? hb->col_readbase + c0 : nullptr;
+    sub.col_refpos = hb->col_refpos ? hb->col_refpos + c0 : nullptr;
+    sub.start_clip = hb->start_clip + r0; sub.end_clip = hb->end_clip + r0;
+    sub.contig = hb->contig + r0; sub.strand = hb->strand + r0;
+    {
+      SlotSwap slot(ctx, (k & 1) != 0);
+      cudaStream_t s = ctx->stream;
+      DM_CUDA(ctx, cudaStreamSynchronize(s));       // this slot's previous part is fetched: its buffers are free
+      int64_t nw = 0;
+      DM_TRY(dm_batch_upload(ctx, &sub, &nw));      // returns once the part is staged; the other slot keeps computing
+      h2d += ctx->h2d_bytes;
+      dm_dev_batch& b = ctx->b;
+      DM_CUDA(ctx, cudaEventRecord(ev[4 * k + 0], s));
+      DM_TRY(dm_launch_prepare(ctx));
+      b.prepared = true;
+      DM_CUDA(ctx, cudaEventRecord(ev[4 * k + 1], s));
+      DM_TRY(run_lstm(ctx, b));
+      DM_CUDA(ctx, cudaEventRecord(ev[4 * k + 2], s));
+      DM_TRY(dm_launch_mask_rejected(ctx));
+      if (accumulate) DM_TRY(dm_launch_accumulate(ctx));
+      DM_CUDA(ctx, cudaEventRecord(ev[4 * k + 3], s));
+      part[(size_t)k].r0 = r0; part[(size_t)k].m = m; part[(size_t)k].nw = nw; part[(size_t)k].win0 = win_base;
+      win_base += nw;
+    }
+    if (k > 0) DM_TRY(fetch(k - 1));
+  }
+  DM_TRY(fetch(np - 1));
+  DM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  DM_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+  ctx->lstm_ms = 0.f;
+  for (int k = 0; k < np; ++k) {
+    float ms = 0.f;
+    DM_CUDA(ctx, cudaEventElapsedTime(&ms, ev[4 * k + 1], ev[4 * k + 2]));
+    ctx->lstm_ms += ms;
+  }
+  DM_CUDA(ctx, cudaEventElapsedTime(&ctx->total_ms, ev[0], ev[4 * (np - 1) + 3]));
+  ctx->h2d_bytes = h2d;
+  return DM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dm_set_pipeline(dm_ctx* ctx, int parts) {
+  if (!ctx) return DM_ERR_ARG;
+  if (parts < 0 || parts > 64) return fail(ctx, DM_ERR_ARG, "dm_set_pipeline: parts must be in [0, 64]");
+  ctx->pipeline_parts = parts;
+  return DM_OK;
+}
+
 int dm_detect_batch(dm_ctx* ctx, const dm_batch* hb, float* p1_out, uint8_t* pred_out, int32_t* status_out) {
   if (!ctx || !hb) return DM_ERR_ARG;
+  // large batches are cut into sub-batches whose transfers hide under each other's kernels
+  int parts = ctx->pipeline_parts;
+  if (parts == 0) {
+    const int64_t n_ev = (hb->n_reads > 0 && hb->ev_off) ? hb->ev_off[hb->n_reads] : 0;
+    parts = (int)std::min<int64_t>(8, n_ev / 1500000);        // >= 1.5 M events (~15 ms of BiLSTM) per part
+  }
+  if (parts >= 2 && hb->n_reads >= 2) return detect_batch_pipelined(ctx, hb, parts, p1_out, pred_out, status_out);
   int64_t nw = 0;
   DM_TRY(dm_batch_upload(ctx, hb, &nw));
   DM_TRY(dm_detect_resident(ctx, ctx->cells != nullptr));

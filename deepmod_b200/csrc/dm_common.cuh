@@ -86,6 +86,10 @@ struct dm_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   dm_dev_weights w{};
   dm_dev_batch b{};               // the uploaded read batch
+  dm_dev_batch b2{};              // second slot of the pipelined dm_detect_batch (upload k+1 under compute k)
+  cudaStream_t stream2 = nullptr;
+  int pipeline_parts = 0;         // dm_set_pipeline: 0 = by batch size, 1 = off, n = always n sub-batches
+  void* scratch2 = nullptr; size_t scratch2_bytes = 0;
   dm_dev_batch fw{};              // dm_forward_windows' own table (explicit [n,21,7] windows)
   float* fw_x = nullptr; int64_t fw_x_cap = 0;
   size_t h2d_bytes = 0;           // bytes the last dm_batch_upload moved

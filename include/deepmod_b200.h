@@ -160,6 +160,12 @@ int dm_write_cluster_bed(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* 
  * status_out[n_reads] receives dm_read_status.  Any output may be NULL. */
 int dm_detect_batch(dm_ctx* ctx, const dm_batch* b, float* p1_out, uint8_t* pred_out,
                     int32_t* status_out);
+/* dm_detect_batch cuts a large batch into contiguous read ranges and alternates them between two
+ * device slots / streams, so the host<->device copies of one range run under the kernels of the
+ * other (results are identical: reads are independent, the accumulator is a sum).  parts: 0 = decide
+ * by batch size (default), 1 = never, n = always n ranges.  After dm_detect_batch the resident
+ * batch (dm_detect_resident, dm_build_windows, ...) is unspecified; use dm_batch_upload for those. */
+int dm_set_pipeline(dm_ctx* ctx, int parts);
 
 /* ---- event-table front-end: raw signal -> per-event statistics ----------------------------------------- */
 /* mnormalized (myDetect.py:266-282) + the per-event mean / stdv loop of getFast5Info (:334-343) for a batch of

@@ -136,6 +136,28 @@ def test_accumulate_is_additive_and_clearable(capi, golden_batch):
         assert all(np.array_equal(x, y) for x, y in zip(a, d))
 
 
+@pytest.mark.parametrize("precision", [0, 1])
+def test_pipelined_detect_equals_single_pass(capi, golden_batch, precision):
+    """dm_detect_batch cut into sub-batches over two streams (dm_set_pipeline): same probabilities, labels,
+    statuses and per-position counts as one pass; reads are independent and the reducer is a sum."""
+    batch, names, lens = golden_batch
+    with make_ctx(capi, "conmodC_P100", precision) as ctx:
+        ctx.set_genome(lens, "C")
+        ctx.set_pipeline(1)
+        p1, pred, status = ctx.detect_batch(batch)
+        want = {(ci, s): ctx.hist_nonzero(ci, s) for ci in range(len(names)) for s in "+-"}
+        for parts in (2, 3, 7, 64):
+            ctx.hist_clear()
+            ctx.set_pipeline(parts)
+            q1, qred, qstatus = ctx.detect_batch(batch)
+            assert np.array_equal(p1, q1) and np.array_equal(pred, qred) and np.array_equal(status, qstatus), parts
+            for key, w in want.items():
+                got = ctx.hist_nonzero(*key)
+                assert all(np.array_equal(x, y) for x, y in zip(w, got)), (parts, key)
+        # outputs are optional in the pipelined path too
+        ctx.detect_batch(batch, want_p1=False, want_pred=False)
+
+
 def test_empty_and_rejected_only_batches(capi, golden_batch):
     from deepmod_b200 import synth
     batch, names, lens = golden_batch
