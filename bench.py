@@ -258,31 +258,45 @@ def main():
     cells = ctx.hist_tensor() if world > 1 else None
 
     # ---- device-resident throughput (value) ----
+    # timed on the device: the library brackets every step with CUDA events on its own stream (dm_last_timing),
+    # the exchange step is bracketed with events on torch's stream; the wall clock is kept as a cross-check
     for _ in range(args.warmup):
         ctx.detect_resident(True)
+    if world > 1:
+        dist.all_reduce(cells, op=dist.ReduceOp.SUM)      # warm-up of the exchange step (NCCL sets up its channels lazily)
     ctx.hist_clear()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.launches
-    lstm_ms = []
+    lstm_ms, step_ms = [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ctx.detect_resident(True)
-        lstm_ms.append(ctx.last_timing()[0])
+        lt, tt_ = ctx.last_timing()
+        lstm_ms.append(lt)
+        step_ms.append(tt_)
+    reduce_ms = 0.0
     if world > 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         dist.all_reduce(cells, op=dist.ReduceOp.SUM)      # the job's single exchange step
+        e1.record()
+        e1.synchronize()
+        reduce_ms = e0.elapsed_time(e1)
     barrier()
-    dt = time.perf_counter() - t0
+    wall = time.perf_counter() - t0
+    dt = (float(np.sum(step_ms)) + reduce_ms) * 1e-3
     launches = ctx.launches - l0
     clocks = sampler.stop() if sampler else None
     p1, pred, status = ctx.fetch(pb.n_windows, pb.n_reads)
     n_ok = int(pb.n_windows_per_read[status == 0].sum())
-    tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+    tt = torch.tensor([dt, wall, reduce_ms], device="cuda", dtype=torch.float64)
     tot = torch.tensor([float(n_ok)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dt_max, total_bases = float(tt.item()), float(tot.item())
+    dt_max, wall_max, reduce_max = (float(x) for x in tt.tolist())
+    total_bases = float(tot.item())
     value = total_bases * args.steps / dt_max / 1e6
 
     # ---- end to end through the host-buffer call (e2e) ----
@@ -352,6 +366,9 @@ def main():
                                    % (args.reads, n_ok, "bf16 tcgen05 tensor-core" if prec else "fp32 parity"),
                        "reads_per_gpu": args.reads, "bases_per_gpu_step": n_ok, "parallelism": "reads sharded x%d, 1 NCCL sum of the accumulator" % world,
                        "l2": "inputs larger than L2 (feature table %.0f MB per step)" % (pb.n_windows * 64 / 1e6)},
+            "timing": {"how": "CUDA events on the library's stream around every step (dm_last_timing) + events around the "
+                              "NCCL sum, max over ranks", "wall_ms_per_step": 1e3 * wall_max / args.steps,
+                       "exchange_ms": reduce_max},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": d2h},
             "roofline": roof}
