@@ -39,11 +39,18 @@ def load_weights():
         return {k: z[k] for k in z.files}
 
 
-def make_workload(rank, n_reads=N_READS):
+def make_workload(rank, n_reads=N_READS, target_windows=None):
+    """Rank 0: the configs[0]/[1] read set.  Other ranks: their own reads (own seeds), cut to the same number of
+    windows as rank 0's shard - the job shards reads into ranges balanced by sum(Lmap)."""
     from deepmod_b200 import synth
     genome = synth.make_genome([GENOME_LEN], seed=1)
-    batch = synth.make_reads(genome, n_reads, seed=2 + 1000 * rank, align_seed=3 + 1000 * rank, mean_len=8000,
+    n_gen = n_reads if target_windows is None else int(n_reads * 1.15) + 8
+    batch = synth.make_reads(genome, n_gen, seed=2 + 1000 * rank, align_seed=3 + 1000 * rank, mean_len=8000,
                              len_lo=600, len_hi=60000, max_clip=30)
+    if target_windows is not None:
+        cum = np.cumsum(synth.n_windows(batch))
+        keep = int(np.searchsorted(cum, target_windows, side="right"))
+        batch = synth.take_reads(batch, np.arange(max(keep, 1), dtype=np.int64))
     return batch
 
 
@@ -249,7 +256,18 @@ def main():
 
     weights = load_weights()
     model = checkpoint.Model.from_dict(weights)
-    batch = make_workload(rank, args.reads)
+    if world > 1:
+        # every rank's shard holds the same number of windows (within one read) as rank 0's
+        from deepmod_b200 import synth
+        tgt = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if rank == 0:
+            batch = make_workload(0, args.reads)
+            tgt[0] = int(synth.n_windows(batch).sum())
+        dist.broadcast(tgt, 0)
+        if rank != 0:
+            batch = make_workload(rank, args.reads, int(tgt.item()))
+    else:
+        batch = make_workload(rank, args.reads)
     prec = capi.BF16 if args.precision == "bf16" else capi.FP32
     ctx = capi.Context(model, device=local, precision=prec)
     ctx.set_genome([GENOME_LEN], "C")

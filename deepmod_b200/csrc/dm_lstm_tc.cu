@@ -48,6 +48,9 @@ constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand du
 #ifndef TC_PREFETCH
 #define TC_PREFETCH 1      // 1: the accumulator load of chunk j+1 is issued before the stores of chunk j
 #endif
+#ifndef TC_T0SKIP
+#define TC_T0SKIP 1        // 1: no forget-gate tanh at t == 0 (c_prev == 0); 0: no special case (one branch less per chunk)
+#endif
 #ifndef TC_SKEW
 #define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
 #endif
@@ -552,7 +555,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
                 const float tj = tanh_mufu(__uint_as_float(v[4 * u + 1]));
                 const float to = tanh_mufu(__uint_as_float(v[4 * u + 3]));
                 const float si = fmaf(ti, 0.5f, 0.5f), so = fmaf(to, 0.5f, 0.5f);
-                if (t == 0) {                         // c_prev == 0: the forget gate cannot matter
+                if (TC_T0SKIP && t == 0) {            // c_prev == 0: the forget gate cannot matter
                   cn[k] = si * tj;
                 } else {
                   const float sf = fmaf(tanh_mufu(__uint_as_float(v[4 * u + 2])), 0.5f, 0.5f);
