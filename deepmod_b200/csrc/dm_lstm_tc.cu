@@ -51,6 +51,9 @@ constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand du
 #ifndef TC_T0SKIP
 #define TC_T0SKIP 1        // 1: no forget-gate tanh at t == 0 (c_prev == 0); 0: no special case (one branch less per chunk)
 #endif
+#ifndef TC_UNIWARP
+#define TC_UNIWARP 1       // warp index through a shuffle (provably warp-uniform for the compiler)
+#endif
 #ifndef TC_SKEW
 #define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
 #endif
@@ -260,7 +263,9 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   max_steps = DBG ? (max_steps & 0xFF) : 2 * TC_STEPS_PER_DIR;
   unsigned long long* ts = (DBG && dbg != nullptr && blockIdx.x == 0) ? reinterpret_cast<unsigned long long*>(dbg + OFF_W) : nullptr;
 #define TS(idx) do { if (DBG && ts) ts[(idx)] = clock64(); } while (0)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the warp index goes through a shuffle so that the compiler KNOWS it is warp-uniform: role branches are then
+  // uniform and per-warp quantities (column group, descriptors, barrier addresses) can live in uniform registers
+  const int tid = threadIdx.x, warp = TC_UNIWARP ? __shfl_sync(0xffffffffu, tid >> 5, 0) : tid >> 5, lane = tid & 31;
   const uint32_t crank = PAIR ? cluster_rank() : 0u;      // 0 = leader (issues the MMAs of the pair)
   const bool leader = crank == 0;
   // persistent: this CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (a pair walks tile pairs);
