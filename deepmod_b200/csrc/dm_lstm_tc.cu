@@ -46,13 +46,17 @@ constexpr int TC_HTILE = TC_HCOLS * TC_ACOL;
 constexpr int TC_STEPS_PER_DIR = 33;
 constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand dump
 #ifndef TC_PREFETCH
-#define TC_PREFETCH 1      // 1: the accumulator load of chunk j+1 is issued before the stores of chunk j
+#define TC_PREFETCH 2      // 1: the accumulator load of chunk j+1 is issued before the stores of chunk j
+                           // 2: also across cell-steps wherever the next step's MMAs cannot depend on this one
 #endif
 #ifndef TC_T0SKIP
 #define TC_T0SKIP 1        // 1: no forget-gate tanh at t == 0 (c_prev == 0); 0: no special case (one branch less per chunk)
 #endif
 #ifndef TC_UNIWARP
 #define TC_UNIWARP 1       // warp index through a shuffle (provably warp-uniform for the compiler)
+#endif
+#ifndef TC_EARLYTEST
+#define TC_EARLYTEST 0     // 1: probe the next chunk's barrier (non-blocking) before the cell update
 #endif
 #ifndef TC_SKEW
 #define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
@@ -484,6 +488,8 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
     uint32_t tslot = 0, tuse = 0;
     const int ts0 = 1024 + (warp ? 2048 : 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sgrp * 16;
+    uint32_t v[16];           // accumulator chunk: 4 units x (i, j, f, o)
+    bool have = false;        // v already holds the in-flight load of the next chunk (TC_PREFETCH == 2)
     for (int it = 0; it < n_iter; ++it) {
     const int64_t win0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * DM_TILE_M;
     const int G0 = it * 2 * TC_STEPS_PER_DIR;
@@ -527,8 +533,10 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             const bool done = mbar_test(bar0 + 8 * (BAR_TFULL + s3), u3 & 1) && mbar_test(bar0 + 8 * (BAR_TFULL + s4), u4 & 1);
             direct = __shfl_sync(0xffffffffu, (int)done, 0) != 0;
           }
-          uint32_t v[16];
-          if (TC_PREFETCH) {
+          // may the first chunk of the NEXT cell-step be loaded before this step is reported done?  Only if its
+          // MMAs cannot wait for this step's hidden state (the wavefront corners and direction ends do)
+          const bool cross = TC_PREFETCH == 2 && !(d == 0 || (d == 11 && l == 2) || d == 12) && g + 1 < max_steps;
+          if (TC_PREFETCH && !have) {
             mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
             tc_fence_after();
             tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
@@ -547,6 +555,9 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_TEMPTY + tslot));      // CTA-local; the peer's relay forwards
             if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
             if (stamp) TS(ts0 + g * 16 + 3 * j + 2);
+            // early non-blocking probe of the next chunk's barrier: its latency hides behind the cell update
+            const bool nxt = TC_PREFETCH && (j + 1 < TC_NCHUNK || cross);       // (tslot, tuse) now name the next chunk
+            const bool rdy = TC_EARLYTEST && nxt && __all_sync(0xffffffffu, mbar_test(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1));
             float hn[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
@@ -570,10 +581,9 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
               }
               cst[l][j][p] = __floats2half2_rn(cn[0], cn[1]);
             }
-            if (TC_PREFETCH && j + 1 < TC_NCHUNK) {
+            if (nxt) {
               // v is dead: the next chunk's barrier probe and TMEM load overlap this chunk's packing and stores
-              // (same cell-step only: its MMAs never depend on what this step's epilogue still has to write)
-              mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+              if (!rdy) mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
               tc_fence_after();
               tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
             }
@@ -632,6 +642,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           __syncwarp();
           if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_HDONE + (g & 1)));         // CTA-local; the peer's relay forwards
           if (stamp) TS(ts0 + g * 16 + 15);
+          have = cross;
           ++g;
         }
       }
