@@ -78,10 +78,20 @@ class ClockSampler(object):
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Start of the timed region: only samples written from here on count (nvidia-smi has been running
+        since before the warm-up, so its start-up time cannot eat the window)."""
+        try:
+            self.fh.flush()
+            self.offset = os.path.getsize(self.path)
+        except Exception:
+            self.offset = 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
+        time.sleep(0.12)          # let the last 100 ms sample of the region land
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -91,7 +101,10 @@ class ClockSampler(object):
         sm, mx, power, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         try:
-            for line in open(self.path):
+            with open(self.path) as fh:
+                fh.seek(getattr(self, "offset", 0))
+                lines = fh.read().splitlines()
+            for line in lines:
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 8:
                     continue
@@ -254,6 +267,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None     # running long before the timed region (see mark())
     weights = load_weights()
     model = checkpoint.Model.from_dict(weights)
     if world > 1:
@@ -284,7 +298,8 @@ def main():
         dist.all_reduce(cells, op=dist.ReduceOp.SUM)      # warm-up of the exchange step (NCCL sets up its channels lazily)
     ctx.hist_clear()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     l0 = ctx.launches
     lstm_ms, step_ms = [], []
     t0 = time.perf_counter()

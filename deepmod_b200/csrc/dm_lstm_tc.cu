@@ -58,6 +58,9 @@ constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand du
 #ifndef TC_EARLYTEST
 #define TC_EARLYTEST 0     // 1: probe the next chunk's barrier (non-blocking) before the cell update
 #endif
+#ifndef TC_LDSPLIT
+#define TC_LDSPLIT 1       // 1: the next chunk's accumulator comes in two x8 loads, the first one half a chunk earlier
+#endif
 #ifndef TC_SKEW
 #define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
 #endif
@@ -152,6 +155,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // same, with the loaded registers as in/out operands: no consumer of v can be scheduled above the wait
@@ -541,6 +553,32 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             tc_fence_after();
             tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
           }
+          // h of chunk jj (units 20 jj + 4 sgrp ..+3): classifier partial, bf16 pack, store into the next A operand
+          auto emit = [&](int jj, const float (&hn)[4]) {
+            if (l == 2 && t == 10) {
+              const float* cw = s_cls + dir * DM_HIDDEN + 20 * jj + 4 * sgrp;
+              cls_acc += hn[0] * cw[0] + hn[1] * cw[1] + hn[2] * cw[2] + hn[3] * cw[3];
+            }
+            // core column u0/8, byte (u0%8)*2 of the row's 16 B
+            const int u0 = 20 * jj + 4 * sgrp;
+            unsigned char* dst = smem + htile + (u0 >> 3) * TC_ACOL + row_off + (u0 & 7) * 2;
+            const uint32_t h01 = pack_bf16(hn[0], hn[1]), h23 = pack_bf16(hn[2], hn[3]);
+            if (l == 2 && !direct) {
+              hkeep[jj][0] = h01; hkeep[jj][1] = h23;
+              if (jj == TC_NCHUNK - 1) {
+#pragma unroll
+                for (int j2 = 0; j2 < TC_NCHUNK; ++j2) {
+                  const int uu = 20 * j2 + 4 * sgrp;
+                  *reinterpret_cast<uint2*>(smem + htile + (uu >> 3) * TC_ACOL + row_off + (uu & 7) * 2) =
+                      make_uint2(hkeep[j2][0], hkeep[j2][1]);
+                }
+              }
+            } else if (jj == TC_NCHUNK - 1 && sgrp == 4) {
+              *reinterpret_cast<uint4*>(dst) = make_uint4(h01, h23, lows.x, lows.y);
+            } else {
+              *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
+            }
+          };
 #pragma unroll
           for (int j = 0; j < TC_NCHUNK; ++j) {
             if (stamp) TS(ts0 + g * 16 + 3 * j);
@@ -558,57 +596,61 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             // early non-blocking probe of the next chunk's barrier: its latency hides behind the cell update
             const bool nxt = TC_PREFETCH && (j + 1 < TC_NCHUNK || cross);       // (tslot, tuse) now name the next chunk
             const bool rdy = TC_EARLYTEST && nxt && __all_sync(0xffffffffu, mbar_test(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1));
-            float hn[4] = {0.f, 0.f, 0.f, 0.f};
+            // cell update of chunk j
+            float cn[4] = {0.f, 0.f, 0.f, 0.f}, so[4] = {0.f, 0.f, 0.f, 0.f};
+            if (!dbg_nomath) {
 #pragma unroll
-            for (int p = 0; p < 2; ++p) {
-              if (dbg_nomath) break;
-              const float2 cp = __half22float2(cst[l][j][p]);
-              float cn[2];
+              for (int p = 0; p < 2; ++p) {
+                const float2 cp = __half22float2(cst[l][j][p]);
 #pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                const int u = 2 * p + k;
-                const float ti = tanh_mufu(__uint_as_float(v[4 * u + 0]));
-                const float tj = tanh_mufu(__uint_as_float(v[4 * u + 1]));
-                const float to = tanh_mufu(__uint_as_float(v[4 * u + 3]));
-                const float si = fmaf(ti, 0.5f, 0.5f), so = fmaf(to, 0.5f, 0.5f);
-                if (TC_T0SKIP && t == 0) {            // c_prev == 0: the forget gate cannot matter
-                  cn[k] = si * tj;
-                } else {
-                  const float sf = fmaf(tanh_mufu(__uint_as_float(v[4 * u + 2])), 0.5f, 0.5f);
-                  cn[k] = fmaf(k == 0 ? cp.x : cp.y, sf, si * tj);
+                for (int k = 0; k < 2; ++k) {
+                  const int u = 2 * p + k;
+                  const float ti = tanh_mufu(__uint_as_float(v[4 * u + 0]));
+                  const float tj = tanh_mufu(__uint_as_float(v[4 * u + 1]));
+                  const float to = tanh_mufu(__uint_as_float(v[4 * u + 3]));
+                  const float si = fmaf(ti, 0.5f, 0.5f);
+                  so[u] = fmaf(to, 0.5f, 0.5f);
+                  if (TC_T0SKIP && t == 0) {            // c_prev == 0: the forget gate cannot matter
+                    cn[u] = si * tj;
+                  } else {
+                    const float sf = fmaf(tanh_mufu(__uint_as_float(v[4 * u + 2])), 0.5f, 0.5f);
+                    cn[u] = fmaf(k == 0 ? cp.x : cp.y, sf, si * tj);
+                  }
+                  if (TC_LDSPLIT == 2 && nxt && u < 3) {
+                    // unit u has read its four gate columns: the next chunk's unit u follows at once
+                    if (u == 0) {
+                      if (!rdy) mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+                      tc_fence_after();
+                    }
+                    tc_ld4(t_lane + tslot * TC_CHUNK_N + 4 * u, v + 4 * u);
+                  }
                 }
-                hn[u] = tanh_mufu(cn[k]) * so;
+                cst[l][j][p] = __floats2half2_rn(cn[2 * p], cn[2 * p + 1]);
+                if (TC_LDSPLIT == 1 && p == 0 && nxt) {
+                  // units 0, 1 have read their half of v: the next chunk's first 8 columns start flying now
+                  if (!rdy) mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+                  tc_fence_after();
+                  tc_ld8(t_lane + tslot * TC_CHUNK_N, v);
+                }
               }
-              cst[l][j][p] = __floats2half2_rn(cn[0], cn[1]);
             }
             if (nxt) {
               // v is dead: the next chunk's barrier probe and TMEM load overlap this chunk's packing and stores
-              if (!rdy) mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
-              tc_fence_after();
-              tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
-            }
-            if (l == 2 && t == 10) {
-              const float* cw = s_cls + dir * DM_HIDDEN + 20 * j + 4 * sgrp;
-              cls_acc += hn[0] * cw[0] + hn[1] * cw[1] + hn[2] * cw[2] + hn[3] * cw[3];
-            }
-            // units u0..u0+3, u0 = 20 j + 4 sgrp: core column u0/8, byte (u0%8)*2 of the row's 16 B
-            const int u0 = 20 * j + 4 * sgrp;
-            unsigned char* dst = smem + htile + (u0 >> 3) * TC_ACOL + row_off + (u0 & 7) * 2;
-            const uint32_t h01 = pack_bf16(hn[0], hn[1]), h23 = pack_bf16(hn[2], hn[3]);
-            if (l == 2 && !direct) {
-              hkeep[j][0] = h01; hkeep[j][1] = h23;
-              if (j == TC_NCHUNK - 1) {
-#pragma unroll
-                for (int jj = 0; jj < TC_NCHUNK; ++jj) {
-                  const int uu = 20 * jj + 4 * sgrp;
-                  *reinterpret_cast<uint2*>(smem + htile + (uu >> 3) * TC_ACOL + row_off + (uu & 7) * 2) =
-                      make_uint2(hkeep[jj][0], hkeep[jj][1]);
-                }
+              if (TC_LDSPLIT == 1 && !dbg_nomath) {
+                tc_ld8(t_lane + tslot * TC_CHUNK_N + 8, v + 8);
+              } else if (TC_LDSPLIT == 2 && !dbg_nomath) {
+                tc_ld4(t_lane + tslot * TC_CHUNK_N + 12, v + 12);
+              } else {
+                if (!rdy) mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+                tc_fence_after();
+                tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
               }
-            } else if (j == TC_NCHUNK - 1 && sgrp == 4) {
-              *reinterpret_cast<uint4*>(dst) = make_uint4(h01, h23, lows.x, lows.y);
-            } else {
-              *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
+            }
+            {
+              float hn[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) hn[u] = dbg_nomath ? 0.f : tanh_mufu(cn[u]) * so[u];
+              emit(j, hn);
             }
           }
           if (l == 0 && sgrp == 0 && t + 2 <= 10)
