@@ -61,6 +61,10 @@ constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand du
 #ifndef TC_LDSPLIT
 #define TC_LDSPLIT 1       // 1: the next chunk's accumulator comes in two x8 loads, the first one half a chunk earlier
 #endif
+#ifndef TC_T0TRIM
+#define TC_T0TRIM 1        // 1: at t == 0 (h_prev == 0) the MMAs over the own hidden tile are not issued, and a direction
+                           //    re-initialisation zeroes only the three core columns those steps still read
+#endif
 #ifndef TC_SKEW
 #define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
 #endif
@@ -320,7 +324,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   const uint32_t row_off = (uint32_t)((row >> 3) * 128 + (row & 7) * 16);
 
   // direction init: zero the hidden tiles, stage x(0), x(1) and the step-0 extras of h0[1]
-  auto dir_init = [&](int dir) {
+  auto dir_init = [&](int dir, bool full) {
     const int et = tid;
     // the global loads go first so that their latency hides behind the zeroing and the barrier
     uint4 v = make_uint4(0, 0, 0, 0);
@@ -331,8 +335,18 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
       v.x = e.x; v.y = e.y;
     }
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (int i = et; i < (5 * TC_HTILE) / 16; i += TC_EPI_THREADS)
-      *reinterpret_cast<uint4*>(smem + OFF_H0 + i * 16) = z;
+    if (full || !TC_T0TRIM) {
+      // (the very first time also for what no step writes before it is multiplied by a zero weight: unused K slots)
+      for (int i = et; i < (5 * TC_HTILE) / 16; i += TC_EPI_THREADS)
+        *reinterpret_cast<uint4*>(smem + OFF_H0 + i * 16) = z;
+    } else if (et < 384) {
+      // every tile is rewritten by this direction's own steps before it is read, except what the t = 0 steps read of
+      // h(-1): units 96..99 next to layer 0's step-0 extras (h0[1] column 12) and the column that shares a K = 16 MMA
+      // with the last column of the tile below (h1[1] column 0, h2 column 0)
+      const int c = et >> 7;
+      const uint32_t col = c == 0 ? OFF_H0 + TC_HTILE + 12 * TC_ACOL : c == 1 ? OFF_H1 + TC_HTILE : OFF_H2;
+      *reinterpret_cast<uint4*>(smem + col + (et & 127) * 16) = z;
+    }
     epi_bar();
     if (et < 256) {
       const int r = et & 127, tau = et >> 7;
@@ -351,7 +365,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   };
   if (warp < TC_EPI_WARPS) {
     for (int i = tid; i < 5 * 128; i += TC_EPI_THREADS) s_part[i] = 0.f;
-    dir_init(0);
+    dir_init(0, true);
   }
   tc_fence_before();
   __syncthreads();
@@ -450,7 +464,11 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
         // descriptor (low word) per K=16 step, shared by the five N-chunks of the step
         uint32_t base0, base1;
         const int n0 = l == 0 ? 1 : TC_HCOLS;
-        const int nk16 = l == 0 ? 7 : 13;
+        // t == 0: h(-1) == 0, the K steps over the own hidden tile drop out.  Layers 1, 2 keep the first 7 (the 7th
+        // pairs the last column of the tile below with own column 0, which is zero); layer 0 keeps ONE: the x
+        // column paired with own column 12 (bias carriers and the low feature halves)
+        const bool t0 = TC_T0TRIM && t == 0;
+        const int nk16 = l == 0 ? (t0 ? 1 : 7) : (t0 ? 7 : 13);
         if (l == 0)      { base0 = sbase + OFF_X + (t & 1) * TC_ACOL;   base1 = sbase + OFF_H0 + ((t + 1) & 1) * TC_HTILE; }
         else if (l == 1) { base0 = sbase + OFF_H0 + (t & 1) * TC_HTILE; base1 = sbase + OFF_H1 + ((t + 1) & 1) * TC_HTILE; }
         else             { base0 = sbase + OFF_H1 + (t & 1) * TC_HTILE; base1 = sbase + OFF_H2; }
@@ -463,13 +481,16 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           const uint32_t a1 = v1 < n0 ? base0 + v1 * TC_ACOL : base1 + (v1 - n0) * TC_ACOL;
           a_lo[i] = ((a0 >> 4) & 0x3FFFu) | (((a1 - a0) >> 4) << 16);
         }
+        if (t0 && l == 0) a_lo[0] = ((base0 >> 4) & 0x3FFFu) | (((base1 + 12 * TC_ACOL - base0) >> 4) << 16);
         for (int j = 0; j < TC_NCHUNK; ++j, ++c) {
           if ((c & 1u) == mine) {
             if (tuse > 0) mbar_wait(bar0 + 8 * (BAR_TEMPTY + tslot), (tuse - 1) & 1);
             if (!dbg_noload) mbar_wait(bar0 + 8 * (BAR_FULL + slot), use & 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + tslot * TC_CHUNK_N;
-            const uint32_t b_lo = (((sbase + OFF_W + slot * G::STAGE) >> 4) & 0x3FFFu) | ((uint32_t)(G::BCOL >> 4) << 16);
+            // (layer 0 at t == 0: weight K columns 0 and 13 of the stage)
+            const uint32_t b_lo = (((sbase + OFF_W + slot * G::STAGE) >> 4) & 0x3FFFu) |
+                                  ((uint32_t)(((t0 && l == 0) ? 13 * G::BCOL : G::BCOL) >> 4) << 16);
             if (!dbg_nomma) {
               _Pragma("unroll")
               for (int i = 0; i < 13; ++i) {
@@ -661,7 +682,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             // BEFORE this step is reported done, because the issuers' next step waits on exactly that
             epi_bar();          // every warp is done with this direction
             if (dir == 0) {
-              if (max_steps > TC_STEPS_PER_DIR) dir_init(1);
+              if (max_steps > TC_STEPS_PER_DIR) dir_init(1, false);
             } else {
               if (sgrp == 0) {
                 float dl = w.cls_db;
@@ -676,7 +697,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
                 for (int i = tid; i < 5 * 128; i += TC_EPI_THREADS) s_part[i] = 0.f;
                 if (tid < DM_TILE_M) s_frow[tid] = win_frow[win0 + (int64_t)gridDim.x * DM_TILE_M + tid];
                 epi_bar();        // next tile's feature rows visible
-                dir_init(0);
+                dir_init(0, false);
               }
             }
           }
