@@ -45,6 +45,8 @@ constexpr int TC_HCOLS = 13;            // 100 units + 4 extra K slots
 constexpr int TC_HTILE = TC_HCOLS * TC_ACOL;
 constexpr int TC_STEPS_PER_DIR = 33;
 constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand dump
+// first of the four hidden units whose gates sit in accumulator columns 16 s .. 16 s + 15 of chunk j
+__host__ __device__ constexpr int tc_unit0(int j, int s);
 #ifndef TC_PREFETCH
 #define TC_PREFETCH 2      // 1: the accumulator load of chunk j+1 is issued before the stores of chunk j
                            // 2: also across cell-steps wherever the next step's MMAs cannot depend on this one
@@ -65,9 +67,18 @@ constexpr int TS_BYTES = 8 * 8192;       // debug timeline behind the operand du
 #define TC_T0TRIM 1        // 1: at t == 0 (h_prev == 0) the MMAs over the own hidden tile are not issued, and a direction
                            //    re-initialisation zeroes only the three core columns those steps still read
 #endif
+#ifndef TC_UNITMAP
+#define TC_UNITMAP 0       // 1: column group s owns units 20 s .. 20 s + 19 (4 per chunk): consecutive chunks complete 16-byte
+                           //    row segments of the hidden tile, which go out as conflict-free 16-byte stores
+                           // 0: chunk j owns units 20 j .. 20 j + 19 (4 per column group): 8-byte stores, 2-way bank conflict
+                           // (measured: 1 is bit-identical and 1.9 % SLOWER despite 12 instead of 20 store wavefronts per
+                           //  warp and step - kept as a switch, off)
+#endif
 #ifndef TC_SKEW
 #define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
 #endif
+
+__host__ __device__ constexpr int tc_unit0(int j, int s) { return TC_UNITMAP ? 20 * s + 4 * j : 20 * j + 4 * s; }
 
 // Geometry of the weight stream: one stage = the B operand of one N-chunk (all K core columns).
 // PAIR = two CTAs of a cluster drive ONE tcgen05.mma.cta_group::2 (M = 256, 128 windows each): every
@@ -574,28 +585,39 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             tc_fence_after();
             tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
           }
-          // h of chunk jj (units 20 jj + 4 sgrp ..+3): classifier partial, bf16 pack, store into the next A operand
+          // h of chunk jj (units tc_unit0(jj, sgrp) ..+3): classifier partial, bf16 pack, store into the next A operand.
+          // With TC_UNITMAP two consecutive chunks fill one 16-byte row segment (8 units): the first half waits in two
+          // registers and the pair leaves as ONE 16-byte store per lane (32 lanes x 16 B contiguous: no bank conflict).
+          // Even column groups pair chunks (0,1), (2,3); odd ones start mid-segment and pair (1,2), (3,4).
+          uint32_t ph0 = 0, ph1 = 0;
           auto emit = [&](int jj, const float (&hn)[4]) {
+            const int u0 = tc_unit0(jj, sgrp);
             if (l == 2 && t == 10) {
-              const float* cw = s_cls + dir * DM_HIDDEN + 20 * jj + 4 * sgrp;
+              const float* cw = s_cls + dir * DM_HIDDEN + u0;
               cls_acc += hn[0] * cw[0] + hn[1] * cw[1] + hn[2] * cw[2] + hn[3] * cw[3];
             }
             // core column u0/8, byte (u0%8)*2 of the row's 16 B
-            const int u0 = 20 * jj + 4 * sgrp;
             unsigned char* dst = smem + htile + (u0 >> 3) * TC_ACOL + row_off + (u0 & 7) * 2;
             const uint32_t h01 = pack_bf16(hn[0], hn[1]), h23 = pack_bf16(hn[2], hn[3]);
+            const bool odd = (sgrp & 1) != 0;
+            const bool pair_lo = TC_UNITMAP && (odd ? (jj == 1 || jj == 3) : (jj == 0 || jj == 2));
+            const bool pair_hi = TC_UNITMAP && (odd ? (jj == 2 || jj == 4) : (jj == 1 || jj == 3));
             if (l == 2 && !direct) {
               hkeep[jj][0] = h01; hkeep[jj][1] = h23;
               if (jj == TC_NCHUNK - 1) {
 #pragma unroll
                 for (int j2 = 0; j2 < TC_NCHUNK; ++j2) {
-                  const int uu = 20 * j2 + 4 * sgrp;
+                  const int uu = tc_unit0(j2, sgrp);
                   *reinterpret_cast<uint2*>(smem + htile + (uu >> 3) * TC_ACOL + row_off + (uu & 7) * 2) =
                       make_uint2(hkeep[j2][0], hkeep[j2][1]);
                 }
               }
             } else if (jj == TC_NCHUNK - 1 && sgrp == 4) {
-              *reinterpret_cast<uint4*>(dst) = make_uint4(h01, h23, lows.x, lows.y);
+              *reinterpret_cast<uint4*>(dst) = make_uint4(h01, h23, lows.x, lows.y);      // units 96..99 + the extras
+            } else if (pair_lo) {
+              ph0 = h01; ph1 = h23;
+            } else if (pair_hi) {
+              *reinterpret_cast<uint4*>(dst - 8) = make_uint4(ph0, ph1, h01, h23);
             } else {
               *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
             }
@@ -810,7 +832,7 @@ void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool 
   for (int j = 0; j < TC_NCHUNK; ++j)
     for (int kc = 0; kc < ncols; ++kc)
       for (int n = 0; n < TC_CHUNK_N; ++n) {
-        const int unit = 20 * j + n / 4, gate = n % 4, col = gate * DM_HIDDEN + unit;
+        const int unit = tc_unit0(j, n / 16) + (n / 4) % 4, gate = n % 4, col = gate * DM_HIDDEN + unit;
         const float scale = gate == 1 ? 1.0f : 0.5f;
         const float bsc = (bias[col] + (gate == 2 ? 1.0f : 0.0f)) * scale;
         const uint16_t bhi = h_bf16(bsc), blo = h_bf16(bsc - h_bf16f(bhi));
