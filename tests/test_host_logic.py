@@ -122,3 +122,23 @@ def test_filter_reads_region_and_conunk(batch):
     for r in idx:
         c0, c1 = b["col_off"][r], b["col_off"][r + 1]
         assert b["contig"][r] == 0 and b["col_refpos"][c0:c1].min() > 10000
+
+
+def test_bench_rank_shards_hold_equal_window_counts():
+    """bench.py at N > 1: every rank generates its own reads and cuts them to rank 0's window count
+    (the job's sharding rule: contiguous read ranges balanced by sum(Lmap))."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("dm_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    base = bench.make_workload(0, 12)
+    target = int(synth.n_windows(base).sum())
+    for rank in (1, 5):
+        mine = bench.make_workload(rank, 12, target)
+        got = int(synth.n_windows(mine).sum())
+        longest = int(synth.n_windows(mine).max())
+        assert got <= target and target - got <= 60000          # within one (clipped-length) read
+        assert not np.array_equal(mine["ev_mean"][:100], base["ev_mean"][:100])      # its own reads
+        capi.PackedBatch(mine)                                   # still a valid packed batch
+        assert longest > 0
