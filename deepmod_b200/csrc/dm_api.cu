@@ -149,7 +149,8 @@ void dm_destroy(dm_ctx* ctx) {
       cudaFree(ctx->w.wtc2[d][l]);
     }
   cudaFree(ctx->w.cls_w); cudaFree(ctx->w.cls_b); cudaFree(ctx->w.cls_d);
-  dm_dev_batch* bs[2] = {&ctx->b, &ctx->fw};
+  if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+  dm_dev_batch* bs[3] = {&ctx->b, &ctx->b2, &ctx->fw};
   for (dm_dev_batch* b : bs) {
     cudaFree(b->ev_off); cudaFree(b->col_off); cudaFree(b->col_refpos);
     cudaFree(b->ev_mean); cudaFree(b->ev_stdv); cudaFree(b->ev_len);
