@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <type_traits>
 
 namespace {
 
@@ -74,6 +75,10 @@ __host__ __device__ constexpr int tc_unit0(int j, int s);
                            // (measured: 1 is bit-identical and 1.9 % SLOWER despite 12 instead of 20 store wavefronts per
                            //  warp and step - kept as a switch, off)
 #endif
+#ifndef TC_INTERLEAVE
+#define TC_INTERLEAVE 1    // 1: the last two cell-steps of a direction are interleaved with the first two of the next one
+                           //    (next direction or next tile), so that NO cell-step depends on its predecessor
+#endif
 #ifndef TC_SKEW
 #define TC_SKEW 0          // SM clocks by which consecutive column groups start a direction later (breaks lockstep)
 #endif
@@ -102,7 +107,7 @@ constexpr int BAR_FULL = 0, BAR_EMPTY = 5, BAR_TFULL = 10, BAR_TEMPTY = 16, BAR_
 constexpr int OFF_TMEM = OFF_BAR + N_BARS * 8;
 constexpr int OFF_PART = OFF_TMEM + 16;                    // float part[5][128]
 constexpr int OFF_FROW = OFF_PART + 5 * 128 * 4;           // int frow[128]
-constexpr int OFF_CLS = OFF_FROW + 128 * 4;                // float cls_d[2][100]
+constexpr int OFF_CLS = OFF_FROW + (TC_INTERLEAVE ? 2 : 1) * 128 * 4;   // float cls_d[2][100]  (frow is per tile parity when interleaved)
 constexpr int TC_SMEM = OFF_CLS + 200 * 4;
 static_assert(TC_SMEM <= 227 * 1024, "shared memory budget");
 
@@ -269,6 +274,30 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return r;
 }
 
+// ---- TC_INTERLEAVE: the global order of cell-steps ----
+// A direction instance (tile, direction) is the sequence S[0..32] of (d, l) in wavefront order.  Within it only S[1]
+// depends on S[0] and S[32] on S[31] at distance one.  Order over instances i = 0..N-1:
+//   S_0[0..30] | S_1[0] S_0[31] S_1[1] S_0[32] S_1[2..30] | S_2[0] S_1[31] S_2[1] S_1[32] S_2[2..30] | ... | S_{N-1}[31] S_{N-1}[32]
+// Every step then reads what steps two or more back have written (except the 2nd and the last step of a CTA's run).
+__device__ __forceinline__ void il_decode(int G, int N, int& inst, int& sidx) {
+  if (G < 31) { inst = 0; sidx = G; return; }
+  const int q = (G - 31) / 33, off = (G - 31) - q * 33, i = q + 1;
+  if (i >= N) { inst = N - 1; sidx = 31 + off; return; }
+  if (off == 0) { inst = i; sidx = 0; }
+  else if (off == 1) { inst = i - 1; sidx = 31; }
+  else if (off == 2) { inst = i; sidx = 1; }
+  else if (off == 3) { inst = i - 1; sidx = 32; }
+  else { inst = i; sidx = off - 2; }
+}
+__device__ __forceinline__ void il_step(int sidx, int& d, int& l) {
+  if (sidx == 0) { d = 0; l = 0; }
+  else if (sidx < 3) { d = 1; l = sidx - 1; }
+  else if (sidx < 30) { d = 2 + (sidx - 3) / 3; l = (sidx - 3) % 3; }
+  else if (sidx == 30) { d = 11; l = 1; }
+  else if (sidx == 31) { d = 11; l = 2; }
+  else { d = 12; l = 2; }
+}
+
 // feature row of time index tau (0..10 in processing order) of a window
 __device__ __forceinline__ int tau_row(int dir, int tau) { return dir == 0 ? tau : DM_WINDOW - 1 - tau; }
 
@@ -385,6 +414,16 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
   const uint32_t tmem_base = *s_tmem;
 
 // walks the 66 cell-steps in wavefront order; BODY sees dir, d, l, t, g
+#if TC_INTERLEAVE
+#define FOR_EACH_STEP(...)                                    \
+  for (int GG = 0; GG < 2 * TC_STEPS_PER_DIR * n_iter; ++GG) { \
+    int inst, sidx, d, l;                                     \
+    il_decode(GG, 2 * n_iter, inst, sidx);                    \
+    il_step(sidx, d, l);                                      \
+    const int dir = inst & 1, t = d - l, g = GG, G0 = 0;      \
+    (void)G0;                                                 \
+    { __VA_ARGS__ } }
+#else
 #define FOR_EACH_STEP(...)                                    \
   for (int it = 0; it < n_iter; ++it) {                       \
     int g = 0;                                                \
@@ -398,6 +437,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           if (g < max_steps) { __VA_ARGS__ }                  \
           ++g;                                                \
         } }
+#endif
 
   if (warp == W_PROD) {
     // ================= weight producer: one stage = one N-chunk of this CTA's gate columns =================
@@ -467,7 +507,11 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
         // fill/drain corners of the wavefront (and across the direction switch)
         const int G = G0 + g;
         if (G >= 2) mbar_wait(bar0 + 8 * (BAR_HDONE + (G & 1)), ((G - 2) >> 1) & 1);
+#if TC_INTERLEAVE
+        const bool wait1 = G == 1 || G == 2 * TC_STEPS_PER_DIR * n_iter - 1;     // the only distance-one dependencies left
+#else
         const bool wait1 = d == 0 || (d == 1 && l == 0) || d == 12;     // d == 0: first step after a (re-)initialisation
+#endif
         if (wait1 && G >= 1) mbar_wait(bar0 + 8 * (BAR_HDONE + ((G - 1) & 1)), ((G - 1) >> 1) & 1);
         tc_fence_after();
         if (mine == 0 && lane == 0) TS(g * 8 + 1);
@@ -534,6 +578,40 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sgrp * 16;
     uint32_t v[16];           // accumulator chunk: 4 units x (i, j, f, o)
     bool have = false;        // v already holds the in-flight load of the next chunk (TC_PREFETCH == 2)
+#if TC_INTERLEAVE
+#define FROW(r) s_frow[(it & 1) * 128 + (r)]
+    const int n_inst = 2 * n_iter, n_steps = 2 * TC_STEPS_PER_DIR * n_iter;
+#pragma unroll
+    for (int l = 0; l < 3; ++l)
+#pragma unroll
+      for (int j = 0; j < TC_NCHUNK; ++j) cst[l][j][0] = cst[l][j][1] = __floats2half2_rn(0.f, 0.f);
+    // one cell-step; the layer is a compile-time constant (the cell state of a layer lives in registers)
+    auto step = [&](auto LC, const int inst, const int sidx, const int d, const int g) {
+      constexpr int l = decltype(LC)::value;
+      const int it = inst >> 1, dir = inst & 1, t = d - l;
+      const int64_t win0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * DM_TILE_M;
+      const bool stamp = false;
+      float cls_acc = 0.f;
+      {
+        {
+          // S[29] = (10, 2): stage what the NEXT direction instance's first steps read (x(0), x(1), the step-0 extras
+          // next to zeroed units 96..99 in h0[1] column 12).  Their last readers (steps S[27], S[28]) have retired,
+          // and this step's "done" arrival is the one the issuers wait for before that instance's first MMA.
+          const bool stage = sidx == 29 && inst + 1 < n_inst && tid < 384;
+          uint4 sv = make_uint4(0, 0, 0, 0);
+          int sfr = 0;
+          if (stage) {
+            const int ndir = (inst + 1) & 1, nit = (inst + 1) >> 1, r = tid & 127;
+            sfr = ndir == 0 ? win_frow[((int64_t)blockIdx.x + (int64_t)nit * gridDim.x) * DM_TILE_M + r] : FROW(r);
+            if (tid < 256) {
+              sv = *reinterpret_cast<const uint4*>(feat_tc + ((int64_t)sfr + tau_row(ndir, tid >> 7)) * 16);
+            } else {
+              const uint2 e = *reinterpret_cast<const uint2*>(feat_tc + ((int64_t)sfr + tau_row(ndir, 0)) * 16 + 8);
+              sv.z = e.x; sv.w = e.y;
+            }
+          }
+#else
+#define FROW(r) s_frow[(r)]
     for (int it = 0; it < n_iter; ++it) {
     const int64_t win0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * DM_TILE_M;
     const int G0 = it * 2 * TC_STEPS_PER_DIR;
@@ -551,14 +629,15 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           const int t = d - l;
           if (t < 0 || t > 10) continue;
           if (g >= max_steps) { ++g; continue; }
+#endif
           // prefetch what this step's epilogue must stage for later steps
           uint4 xnext = make_uint4(0, 0, 0, 0);
           uint2 lows = make_uint2(0, 0);
           if (l == 0) {
             if (sgrp == 0 && t + 2 <= 10)
-              xnext = *reinterpret_cast<const uint4*>(feat_tc + ((int64_t)s_frow[row] + tau_row(dir, t + 2)) * 16);
+              xnext = *reinterpret_cast<const uint4*>(feat_tc + ((int64_t)FROW(row) + tau_row(dir, t + 2)) * 16);
             if (sgrp == 4)   // (1, 1, mean_lo, stdv_lo) of the next time index ride in h0's extras
-              lows = *reinterpret_cast<const uint2*>(feat_tc + ((int64_t)s_frow[row] + tau_row(dir, t + 1 <= 10 ? t + 1 : 10)) * 16 + 8);
+              lows = *reinterpret_cast<const uint2*>(feat_tc + ((int64_t)FROW(row) + tau_row(dir, t + 1 <= 10 ? t + 1 : 10)) * 16 + 8);
           } else if (l == 1) {
             lows = make_uint2(0x3F803F80u, 0u);     // (1, 1, 0, 0): bias carriers for layer 2
           }
@@ -579,7 +658,11 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           }
           // may the first chunk of the NEXT cell-step be loaded before this step is reported done?  Only if its
           // MMAs cannot wait for this step's hidden state (the wavefront corners and direction ends do)
+#if TC_INTERLEAVE
+          const bool cross = TC_PREFETCH == 2 && g != 0 && g < n_steps - 2;
+#else
           const bool cross = TC_PREFETCH == 2 && !(d == 0 || (d == 11 && l == 2) || d == 12) && g + 1 < max_steps;
+#endif
           if (TC_PREFETCH && !have) {
             mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
             tc_fence_after();
@@ -602,7 +685,9 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             const bool odd = (sgrp & 1) != 0;
             const bool pair_lo = TC_UNITMAP && (odd ? (jj == 1 || jj == 3) : (jj == 0 || jj == 2));
             const bool pair_hi = TC_UNITMAP && (odd ? (jj == 2 || jj == 4) : (jj == 1 || jj == 3));
-            if (l == 2 && !direct) {
+            if (TC_INTERLEAVE && l == 2 && t == 10) {
+              // h2(10) only feeds the classifier; storing it would race with the next instance's zeroing of h2 column 0
+            } else if (l == 2 && !direct) {
               hkeep[jj][0] = h01; hkeep[jj][1] = h23;
               if (jj == TC_NCHUNK - 1) {
 #pragma unroll
@@ -699,6 +784,48 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
           if (l == 0 && sgrp == 0 && t + 2 <= 10)
             *reinterpret_cast<uint4*>(smem + OFF_X + (t & 1) * TC_ACOL + row_off) = xnext;
           if (l == 2 && t == 10) s_part[sgrp * 128 + row] += cls_acc;
+#if TC_INTERLEAVE
+          if (stage) {
+            const int r = tid & 127;
+            if (tid < 256) {
+              *reinterpret_cast<uint4*>(smem + OFF_X + (tid >> 7) * TC_ACOL + r * 16) = sv;
+              if (tid < 128 && ((inst + 1) & 1) == 0) s_frow[(((inst + 1) >> 1) & 1) * 128 + r] = sfr;
+            } else {
+              *reinterpret_cast<uint4*>(smem + OFF_H0 + TC_HTILE + 12 * TC_ACOL + r * 16) = sv;
+            }
+          }
+          // the column that shares a K = 16 MMA with the last column of the tile below must read zero at t = 0:
+          // h1[1] column 0 before S[2] = (1,1), h2 column 0 before S[5] = (2,2); their last readers were the
+          // previous instance's S[31] / S[32], which sit just before S[1] / S[2] of this one in the order
+          if (sidx == 1 && tid < 128) *reinterpret_cast<uint4*>(smem + OFF_H1 + TC_HTILE + tid * 16) = make_uint4(0, 0, 0, 0);
+          if (sidx == 2 && tid < 128) *reinterpret_cast<uint4*>(smem + OFF_H2 + tid * 16) = make_uint4(0, 0, 0, 0);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_HDONE + (g & 1)));         // CTA-local; the peer's relay forwards
+          have = cross;
+          if (sidx == 32 && dir == 1) {
+            // both directions' classifier partials of this tile are in: softmax over two classes
+            epi_bar();
+            if (sgrp == 0) {
+              float dl = w.cls_db;
+#pragma unroll
+              for (int s5 = 0; s5 < 5; ++s5) { dl += s_part[s5 * 128 + row]; s_part[s5 * 128 + row] = 0.f; }
+              if (p1_out) p1_out[win0 + row] = 1.0f / (1.0f + __expf(-dl));
+              if (pred_out) pred_out[win0 + row] = dl > 0.f ? 1 : 0;
+            }
+          }
+        }
+      }
+    };
+    for (int GG = 0; GG < n_steps; ++GG) {
+      int inst, sidx, d, l;
+      il_decode(GG, n_inst, inst, sidx);
+      il_step(sidx, d, l);
+      if (l == 0) step(std::integral_constant<int, 0>{}, inst, sidx, d, GG);
+      else if (l == 1) step(std::integral_constant<int, 1>{}, inst, sidx, d, GG);
+      else step(std::integral_constant<int, 2>{}, inst, sidx, d, GG);
+    }
+#else
           if (d == 12) {
             // last cell-step of a direction: everything the next direction / next tile needs is staged
             // BEFORE this step is reported done, because the issuers' next step waits on exactly that
@@ -734,6 +861,8 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
     }
     (void)G0;
     }
+#endif
+#undef FROW
   }
 #undef FOR_EACH_STEP
 #undef TS
