@@ -433,7 +433,7 @@ def main():
     # ---- CPU baseline on the host cores (bounded sample) ----
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        k = pick_sample(batch, 120000)
+        k = pick_sample(batch, 300000)      # ~15 s of CPU work on the GPU box's host cores
         n_cpu, times, _ = cpu_reference_run(weights, batch, 1, 0, k, threads)
         line["cpu_baseline"] = {"value": n_cpu / times[0] / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": "first %d reads (%d bases) of the same read set, one pass, %.1f s" % (k, n_cpu, times[0])}
