@@ -54,14 +54,18 @@ def writes(inst, sidx, l, t, N):
     elif t != 10:                       # h2(10) only feeds the classifier and is not stored
         w[("H2", 0)] = (inst, 2, t)
         w[("H2c0", 0)] = (inst, 2, t)
+    # partial rewrites of a tile: the tile as a whole is no longer the hidden state it was
     if sidx == 29 and inst + 1 < N:     # staging for the next direction instance
         w[("X", 0)] = (inst + 1, "x", 0)
         w[("X", 1)] = (inst + 1, "x", 1)
         w[("H0c12", 1)] = (inst + 1, "ext0")
+        w[("H0", 1)] = "clobbered"
     if sidx == 1:
         w[("H1c0", 1)] = "zero"
+        w[("H1", 1)] = "clobbered"
     if sidx == 2:
         w[("H2c0", 0)] = "zero"
+        w[("H2", 0)] = "clobbered"
     return w
 
 
