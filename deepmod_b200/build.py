@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdeepmod_b200.so")
-SOURCES = ["dm_api.cu", "dm_features.cu", "dm_hist.cu", "dm_lstm_fp32.cu", "dm_lstm_tc.cu", "dm_cluster.cu", "dm_align.cu", "dm_signal.cu"]
+SOURCES = ["dm_api.cu", "dm_features.cu", "dm_hist.cu", "dm_lstm_fp32.cu", "dm_lstm_tc.cu", "dm_cluster.cu", "dm_align.cu", "dm_signal.cu", "dm_reduce.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
@@ -50,7 +50,8 @@ def build(force=False, verbose=False, jobs=None, out=None, extra=None):
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, log))
         objs.append(obj)
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out or LIB] + objs
+    # NCCL is dlopen()ed by dm_reduce.cu (only its header is needed here), hence -ldl
+    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out or LIB] + objs + ["-ldl"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stdout)

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # DEEPMOD_B200_LIB: load another build of the library (tuning sweeps); there is still no CPU fallback
 LIB_PATH = os.environ.get("DEEPMOD_B200_LIB") or os.path.join(HERE, "libdeepmod_b200.so")
 
-FP32, BF16, BF16_1CTA = 0, 1, 2
+FP32, BF16, BF16_1CTA, F16 = 0, 1, 2, 3
 READ_OK, READ_MISMATCH, READ_BAD_ALIGN, READ_LESS_EVENT, READ_NO_MATCH = 0, 1, 2, 3, 4
 STATUS_TEXT = {READ_OK: "", READ_MISMATCH: "Error Does not match",      # myDetect.py:870
                READ_BAD_ALIGN: "Error alignment/event count mismatch",
@@ -26,6 +26,7 @@ _i64p = C.POINTER(C.c_int64)
 _i32p = C.POINTER(C.c_int32)
 _u8p = C.POINTER(C.c_uint8)
 _i8p = C.POINTER(C.c_int8)
+_u64p = C.POINTER(C.c_uint64)
 
 
 class DmWeights(C.Structure):
@@ -67,12 +68,19 @@ SIGNATURES = {
     "dm_set_genome": (C.c_int, [C.c_void_p, C.c_int32, _i64p, C.c_char]),
     "dm_hist_clear": (C.c_int, [C.c_void_p]),
     "dm_hist_device_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _i64p]),
+    "dm_reduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "dm_reduce_unique_id": (C.c_int, [_u8p]),
+    "dm_reduce_comm": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),
+    "dm_hist_merge": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dm_hist_totals": (C.c_int, [C.c_void_p, _u64p, _u64p, _u64p, _u64p]),
+    "dm_last_reduce_ms": (C.c_int, [C.c_void_p, _fp]),
     "dm_hist_nonzero": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _i64p, _i32p, _i32p, _i64p]),
     "dm_write_bed": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_char_p, C.c_char_p, _i64p]),
     "dm_event_stats": (C.c_int, [C.c_void_p, C.c_int32, _i64p, C.POINTER(C.c_int16), _i64p, _i64p, _i64p, _fp, _fp]),
     "dm_set_contig_sequence": (C.c_int, [C.c_void_p, C.c_int32, _u8p, C.c_int64]),
     "dm_align_upload": (C.c_int, [C.c_void_p, C.POINTER(DmSamBatch), _i64p, _i64p]),
     "dm_fetch_alignment": (C.c_int, [C.c_void_p, _i64p, _u8p, _u8p, _i64p, _i32p, _i32p]),
+    "dm_accumulate_records": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _u8p, _u8p, _i64p, _i8p]),
     "dm_hist_load": (C.c_int, [C.c_void_p, C.c_int32, C.c_int8, C.c_int64, _i64p, _i32p, _i32p]),
     "dm_write_merged_bed": (C.c_int, [C.c_void_p, C.c_int32, C.c_char_p, C.c_char_p, _i64p]),
     "dm_cluster_set_sites": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, _i64p, _i8p]),
@@ -155,6 +163,7 @@ class PackedBatch(object):
             if len(self.a[k]) != nc:
                 raise ValueError("%s has %d entries, offsets say %d" % (k, len(self.a[k]), nc))
         self.n_reads = n
+        self.extra = {k: batch.get(k) for k in ("read_id", "aln_pos", "aln_events")}     # optional, host side only
         lmap = np.diff(self.a["ev_off"]) - self.a["start_clip"] - self.a["end_clip"]
         self.n_windows_per_read = np.where(lmap >= 50, lmap, 0).astype(np.int64)   # myDetect.py:702
         self.n_windows = int(self.n_windows_per_read.sum())
@@ -167,6 +176,27 @@ class PackedBatch(object):
 
     def nbytes(self):
         return sum(v.nbytes for v in self.a.values() if v is not None)
+
+
+def reduce_unique_id():
+    """128-byte NCCL id for ``Context.reduce_comm`` (make it on rank 0, share it by any host-side channel)."""
+    lib = load_library()
+    buf = np.zeros(128, np.uint8)
+    rc = lib.dm_reduce_unique_id(_ptr(buf, C.c_uint8))
+    if rc != 0:
+        msg = lib.dm_last_error(None)
+        raise DeepModError("dm_reduce_unique_id failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+    return buf.tobytes()
+
+
+def reduce_contexts(ctxs):
+    """One process driving several GPUs: sum the accumulators of ``ctxs`` (distinct devices) in place."""
+    lib = load_library()
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    rc = lib.dm_reduce(arr, len(ctxs))
+    if rc != 0:
+        msg = lib.dm_last_error(ctxs[0]._h)
+        raise DeepModError("dm_reduce failed (%d): %s" % (rc, msg.decode() if msg else "?"))
 
 
 class Context(object):
@@ -271,6 +301,26 @@ class Context(object):
                                         "strides": None}
         return torch.as_tensor(_Alias(), device=torch.device("cuda", self.device))
 
+    def hist_totals(self):
+        """(sum cov, sum mod, rows, checksum) of the accumulator: what a merge of shards must conserve
+        (rows excepted: two shards may touch the same position)."""
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(self.lib.dm_hist_totals(self._h, *[C.byref(x) for x in v]), "dm_hist_totals")
+        return tuple(int(x.value) for x in v)
+
+    def hist_merge(self, other):
+        """self += other (two contexts of this process with the same genome)."""
+        self._check(self.lib.dm_hist_merge(self._h, other._h), "dm_hist_merge")
+
+    def reduce_comm(self, uid, rank, n_ranks):
+        """One process per GPU: sum the accumulators of all ranks (NCCL all-reduce inside the library).
+        ``uid`` = the 128 bytes of ``reduce_unique_id()`` made on rank 0 (None: reuse the communicator)."""
+        buf = None if uid is None else np.frombuffer(bytes(uid), np.uint8).copy()
+        self._check(self.lib.dm_reduce_comm(self._h, _ptr(buf, C.c_uint8), int(rank), int(n_ranks)), "dm_reduce_comm")
+        ms = C.c_float()
+        self._check(self.lib.dm_last_reduce_ms(self._h, C.byref(ms)), "dm_last_reduce_ms")
+        return ms.value
+
     def hist_nonzero(self, contig, strand):
         n = C.c_int64()
         s = 1 if strand in (1, "+") else -1
@@ -287,6 +337,14 @@ class Context(object):
         s = 1 if strand in (1, "+") else -1
         self._check(self.lib.dm_write_bed(self._h, contig, s, chrom.encode(), path.encode(), C.byref(n)), "dm_write_bed")
         return n.value
+
+    def accumulate_records(self, contig, strand, refbase, readbase, refpos, mod_pred):
+        """Stored per-read records (the `predetail` columns) -> accumulator, myDetect.py:1089-1100."""
+        rb, qb = _arr(refbase, np.uint8), _arr(readbase, np.uint8)
+        rp, mp = _arr(refpos, np.int64), _arr(mod_pred, np.int8)
+        s = 1 if strand in (1, "+") else -1
+        self._check(self.lib.dm_accumulate_records(self._h, contig, s, len(rb), _ptr(rb, C.c_uint8), _ptr(qb, C.c_uint8),
+                                                   _ptr(rp, C.c_int64), _ptr(mp, C.c_int8)), "dm_accumulate_records")
 
     def hist_load(self, contig, strand, pos, cov, mod):
         pos, cov, mod = _arr(pos, np.int64), _arr(cov, np.int32), _arr(mod, np.int32)

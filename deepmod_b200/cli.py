@@ -51,8 +51,10 @@ def build_parser():
     det.add_argument("--outputlayer", default="", choices=["", "sigmoid"], help="how to put activation function for output layer")
     det.add_argument("--Base", type=str, default="C", choices=["A", "C", "G", "T"], help="Interest of bases")
     det.add_argument("--mod_cluster", default=0, choices=[0, 1], help="1: CpG cluster effect; 0: not")
-    det.add_argument("--precision", default="fp32", choices=["fp32", "bf16"],
-                     help="fp32: parity path (<=1e-4 vs the reference graph); bf16: tcgen05 tensor-core path. Default: fp32")
+    det.add_argument("--precision", default="fp32", choices=["fp32", "f16", "bf16"],
+                     help="fp32: parity path (<=1e-4 vs the reference graph); f16 / bf16: tcgen05 tensor-core path with fp16 / bf16 operands. Default: fp32")
+    det.add_argument("--saveDetail", type=int, default=0, choices=[0, 1],
+                     help="1: also write the per-read predictions and their index files (myDetect.py:716-782), the input of a later --predDet 0 run. Default: 0 (the per-position summary is accumulated on the GPU)")
     det.set_defaults(func=mDetect)
     return parser
 
@@ -88,6 +90,7 @@ def options_from_args(margs):
     mo["Base"] = margs.Base
     mo["mod_cluster"] = margs.mod_cluster
     mo["precision"] = margs.precision
+    mo["saveDetail"] = margs.saveDetail
     if mo["Base"] in ("", None):
         err += "\n\t Please provide a base of interest."
     mo["predDet"] = margs.predDet

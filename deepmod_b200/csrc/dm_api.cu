@@ -57,7 +57,13 @@ void pack_fp32(const float* kernel, const float* bias, int layer, std::vector<fl
 
 }  // namespace
 
-void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool pair, std::vector<uint16_t>& img);  // dm_lstm_tc.cu
+void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool pair, bool f16, std::vector<uint16_t>& img);  // dm_lstm_tc.cu
+
+static bool valid_precision(int p) { return p == DM_FP32 || p == DM_BF16 || p == DM_BF16_1CTA || p == DM_F16; }
+static void apply_precision(dm_ctx* ctx, int p) {
+  ctx->precision = p == DM_FP32 ? DM_FP32 : DM_BF16;      // internally: fp32 path or tensor-core path
+  if (p != DM_FP32) { ctx->tc_pair = p != DM_BF16_1CTA; ctx->tc_f16 = p == DM_F16; }
+}
 
 void dm_set_error(dm_ctx* ctx, const std::string& msg) {
   g_error = msg;
@@ -73,7 +79,7 @@ const char* dm_last_error(const dm_ctx* ctx) { return ctx ? ctx->err.c_str() : g
 int dm_create(dm_ctx** out, int device, const dm_weights* w, int precision) {
   if (!out || !w) return fail(nullptr, DM_ERR_ARG, "dm_create: null argument");
   *out = nullptr;
-  if (precision != DM_FP32 && precision != DM_BF16 && precision != DM_BF16_1CTA) return fail(nullptr, DM_ERR_ARG, "dm_create: bad precision");
+  if (!valid_precision(precision)) return fail(nullptr, DM_ERR_ARG, "dm_create: bad precision");
   for (int d = 0; d < 2; ++d)
     for (int l = 0; l < 3; ++l)
       if (!w->kernel[d][l] || !w->bias[d][l]) return fail(nullptr, DM_ERR_ARG, "dm_create: missing weight tensor");
@@ -92,8 +98,7 @@ int dm_create(dm_ctx** out, int device, const dm_weights* w, int precision) {
                                           std::to_string(prop.major) + std::to_string(prop.minor));
   dm_ctx* ctx = new dm_ctx();
   ctx->device = device;
-  ctx->precision = precision == DM_FP32 ? DM_FP32 : DM_BF16;
-  ctx->tc_pair = precision != DM_BF16_1CTA;
+  apply_precision(ctx, precision);
   ctx->sm_count = prop.multiProcessorCount;
   auto bail = [&](int rc) { std::string m = ctx->err; dm_destroy(ctx); g_error = m; return rc; };
 #define DM_CK(call)                                                                         \
@@ -116,12 +121,14 @@ int dm_create(dm_ctx** out, int device, const dm_weights* w, int precision) {
       DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.b32[d][l]), B.size() * sizeof(float)));
       DM_CK(cudaMemcpy(ctx->w.w32[d][l], W.data(), W.size() * sizeof(float), cudaMemcpyHostToDevice));
       DM_CK(cudaMemcpy(ctx->w.b32[d][l], B.data(), B.size() * sizeof(float), cudaMemcpyHostToDevice));
-      dm_tc_pack_weights(w->kernel[d][l], w->bias[d][l], l, false, T);
-      DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.wtc[d][l]), T.size() * sizeof(uint16_t)));
-      DM_CK(cudaMemcpy(ctx->w.wtc[d][l], T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-      dm_tc_pack_weights(w->kernel[d][l], w->bias[d][l], l, true, T);
-      DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.wtc2[d][l]), T.size() * sizeof(uint16_t)));
-      DM_CK(cudaMemcpy(ctx->w.wtc2[d][l], T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      for (int f = 0; f < 2; ++f) {
+        dm_tc_pack_weights(w->kernel[d][l], w->bias[d][l], l, false, f == 1, T);
+        DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.wtc[f][d][l]), T.size() * sizeof(uint16_t)));
+        DM_CK(cudaMemcpy(ctx->w.wtc[f][d][l], T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        dm_tc_pack_weights(w->kernel[d][l], w->bias[d][l], l, true, f == 1, T);
+        DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.wtc2[f][d][l]), T.size() * sizeof(uint16_t)));
+        DM_CK(cudaMemcpy(ctx->w.wtc2[f][d][l], T.data(), T.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+      }
     }
   DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.cls_w), 2 * DM_HIDDEN * 2 * sizeof(float)));
   DM_CK(cudaMalloc(reinterpret_cast<void**>(&ctx->w.cls_b), 2 * sizeof(float)));
@@ -145,8 +152,7 @@ void dm_destroy(dm_ctx* ctx) {
     for (int l = 0; l < 3; ++l) {
       cudaFree(ctx->w.w32[d][l]);
       cudaFree(ctx->w.b32[d][l]);
-      cudaFree(ctx->w.wtc[d][l]);
-      cudaFree(ctx->w.wtc2[d][l]);
+      for (int f = 0; f < 2; ++f) { cudaFree(ctx->w.wtc[f][d][l]); cudaFree(ctx->w.wtc2[f][d][l]); }
     }
   cudaFree(ctx->w.cls_w); cudaFree(ctx->w.cls_b); cudaFree(ctx->w.cls_d);
   if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
@@ -162,7 +168,8 @@ void dm_destroy(dm_ctx* ctx) {
   cudaFree(ctx->scratch2);
   if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   cudaFree(ctx->fw_x);
-  cudaFree(ctx->contig_off_d); cudaFree(ctx->cells); cudaFree(ctx->motif); cudaFree(ctx->genome);
+  dm_reduce_release(ctx);
+  cudaFree(ctx->contig_off_d); cudaFree(ctx->cells); cudaFree(ctx->motif); cudaFree(ctx->genome); cudaFree(ctx->overflow_d);
   cudaFree(ctx->scratch); cudaFree(ctx->hbuf); cudaFree(ctx->dpart);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -175,9 +182,8 @@ void dm_destroy(dm_ctx* ctx) {
 
 int dm_set_precision(dm_ctx* ctx, int precision) {
   if (!ctx) return DM_ERR_ARG;
-  if (precision != DM_FP32 && precision != DM_BF16 && precision != DM_BF16_1CTA) return fail(ctx, DM_ERR_ARG, "dm_set_precision: bad precision");
-  ctx->precision = precision == DM_FP32 ? DM_FP32 : DM_BF16;
-  if (precision != DM_FP32) ctx->tc_pair = precision != DM_BF16_1CTA;
+  if (!valid_precision(precision)) return fail(ctx, DM_ERR_ARG, "dm_set_precision: bad precision");
+  apply_precision(ctx, precision);
   return DM_OK;
 }
 
@@ -377,7 +383,7 @@ int dm_detect_resident(dm_ctx* ctx, int accumulate) {
   DM_CUDA(ctx, cudaStreamSynchronize(s));
   DM_CUDA(ctx, cudaEventElapsedTime(&ctx->lstm_ms, ctx->ev1, ctx->ev2));
   DM_CUDA(ctx, cudaEventElapsedTime(&ctx->total_ms, ctx->ev0, ctx->ev3));
-  return DM_OK;
+  return accumulate ? dm_check_overflow(ctx) : DM_OK;
 }
 
 int dm_fetch_results(dm_ctx* ctx, float* p1_out, uint8_t* pred_out, int32_t* status_out) {
@@ -519,7 +525,7 @@ int detect_batch_pipelined(dm_ctx* ctx, const dm_batch* hb, int parts, float* p1
   }
   DM_CUDA(ctx, cudaEventElapsedTime(&ctx->total_ms, ev[0], ev[4 * (np - 1) + 3]));
   ctx->h2d_bytes = h2d;
-  return DM_OK;
+  return accumulate ? dm_check_overflow(ctx) : DM_OK;
 }
 
 }  // namespace
@@ -612,6 +618,7 @@ int dm_set_genome(dm_ctx* ctx, int32_t n_contigs, const int64_t* contig_len, cha
   cudaFree(ctx->genome); ctx->genome = nullptr;
   cudaFree(ctx->contig_off_d); ctx->contig_off_d = nullptr;
   ctx->n_cells = 2 * off[n_contigs];
+  if (!ctx->overflow_d) DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->overflow_d), sizeof(int)));
   DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->cells), sizeof(unsigned long long) * (size_t)std::max<int64_t>(ctx->n_cells, 1)));
   DM_CUDA(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->contig_off_d), sizeof(int64_t) * off.size()));
   DM_CUDA(ctx, cudaMemcpy(ctx->contig_off_d, off.data(), sizeof(int64_t) * off.size(), cudaMemcpyHostToDevice));
@@ -627,6 +634,7 @@ int dm_hist_clear(dm_ctx* ctx) {
   if (!ctx->cells) return fail(ctx, DM_ERR_STATE, "dm_hist_clear: dm_set_genome not called");
   DM_CUDA(ctx, cudaSetDevice(ctx->device));
   DM_CUDA(ctx, cudaMemsetAsync(ctx->cells, 0, sizeof(unsigned long long) * (size_t)ctx->n_cells, ctx->stream));
+  DM_CUDA(ctx, cudaMemsetAsync(ctx->overflow_d, 0, sizeof(int), ctx->stream));
   DM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return DM_OK;
 }
@@ -667,14 +675,35 @@ int dm_write_bed(dm_ctx* ctx, int32_t contig, int8_t strand, const char* chrom, 
   FILE* fh = fopen(path, "w");
   if (!fh) return fail(ctx, DM_ERR_IO, std::string("dm_write_bed: cannot open ") + path);
   const char sc = strand >= 0 ? '+' : '-';
-  for (size_t i = 0; i < p.size(); ++i) {
-    // myDetect.py:1116-1120: ' '.join([chr, pos, pos+1, base, min(cov,1000), strand, pos, pos+1,
-    //                                 '0,0,0', cov, '%d' % (100*mod/(cov or 1)), mod, '\n'])
+  // myDetect.py:1116-1120: ' '.join([chr, pos, pos+1, base, min(cov,1000), strand, pos, pos+1,
+  //                                 '0,0,0', cov, '%d' % (100*mod/(cov or 1)), mod, '\n'])
+  // formatted by hand into a 1 MB buffer: a whole-genome summary is ~10^8 rows, and fprintf is the bottleneck
+  const size_t clen = strlen(chrom);
+  std::vector<char> buf((size_t)1 << 20);
+  size_t used = 0;
+  auto put_num = [&](long long v) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) buf[used++] = tmp[--n];
+    buf[used++] = ' ';
+  };
+  bool ok = true;
+  for (size_t i = 0; i < p.size() && ok; ++i) {
+    if (used + clen + 256 > buf.size()) { ok = fwrite(buf.data(), 1, used, fh) == used; used = 0; }
     const long long pos = p[i], cov = c[i], mod = m[i];
-    fprintf(fh, "%s %lld %lld %c %lld %c %lld %lld 0,0,0 %lld %lld %lld \n", chrom, pos, pos + 1, ctx->base,
-            cov > 1000 ? 1000LL : cov, sc, pos, pos + 1, cov, (100 * mod) / (cov > 0 ? cov : 1), mod);
+    memcpy(&buf[used], chrom, clen); used += clen; buf[used++] = ' ';
+    put_num(pos); put_num(pos + 1);
+    buf[used++] = ctx->base; buf[used++] = ' ';
+    put_num(cov > 1000 ? 1000LL : cov);
+    buf[used++] = sc; buf[used++] = ' ';
+    put_num(pos); put_num(pos + 1);
+    memcpy(&buf[used], "0,0,0 ", 6); used += 6;
+    put_num(cov); put_num((100 * mod) / (cov > 0 ? cov : 1)); put_num(mod);
+    buf[used++] = '\n';
   }
-  if (fclose(fh) != 0) return fail(ctx, DM_ERR_IO, std::string("dm_write_bed: write failed for ") + path);
+  if (ok && used) ok = fwrite(buf.data(), 1, used, fh) == used;
+  if (fclose(fh) != 0 || !ok) return fail(ctx, DM_ERR_IO, std::string("dm_write_bed: write failed for ") + path);
   return DM_OK;
 }
 
@@ -704,6 +733,9 @@ int dm_debug_tc_windows(dm_ctx* ctx, int64_t n, const float* X, int max_steps, u
 int dm_hist_load(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t n, const int64_t* pos, const int32_t* cov,
                  const int32_t* mod) {
   if (!ctx || (n > 0 && (!pos || !cov || !mod))) return DM_ERR_ARG;
+  for (int64_t i = 0; i < n; ++i)       // the reference's ints are unbounded; ours say so instead of wrapping
+    if (cov[i] < 0 || mod[i] < 0 || (uint64_t)cov[i] > DM_CELL_MASK || (uint64_t)mod[i] > DM_CELL_MASK)
+      return fail(ctx, DM_ERR_OVERFLOW, "dm_hist_load: row " + std::to_string(i) + " has a count outside [0, 2^28)");
   DM_CUDA(ctx, cudaSetDevice(ctx->device));
   return dm_hist_load_rows(ctx, contig, strand, n, pos, cov, mod);
 }

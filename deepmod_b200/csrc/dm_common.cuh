@@ -14,12 +14,17 @@
 #define DM_GATES 400                    // 4 * DM_HIDDEN
 #define DM_TILE_M 128                   // windows per tensor-core tile (UMMA M)
 
-// One accumulator cell per (strand, reference position): three 21-bit counters
-// packed in a uint64 so one atomicAdd updates a column and one NCCL sum merges GPUs.
+// One accumulator cell per (strand, reference position), packed in a uint64 so that one atomic updates a
+// column and one NCCL sum merges GPUs:
+//   bits  0..27  cov   (coverage, < 2^28 = 268 435 456; reaching the limit is REPORTED, never silent:
+//   bits 28..55  mod    k_accumulate raises ctx->overflow, dm_reduce checks max(cov) * ranks before it sums)
+//   bits 56..63  key-created flag of a deletion column (myDetect.py:1093-1094: the key exists although
+//                nothing is counted): 0/1 on one GPU (atomicOr), <= #ranks after the sum, then set back to 0/1
 #define DM_CELL_COV_SHIFT 0
-#define DM_CELL_MOD_SHIFT 21
-#define DM_CELL_DEL_SHIFT 42
-#define DM_CELL_MASK 0x1FFFFFull
+#define DM_CELL_MOD_SHIFT 28
+#define DM_CELL_DEL_SHIFT 56
+#define DM_CELL_MASK 0xFFFFFFFull
+#define DM_CELL_DEL_MASK 0xFFull
 
 // ---- packed weight images ---------------------------------------------------
 // fp32 image per (dir, layer), [K][400]: layer 0 rows = [x0..x6, 0, h0..h99] (108),
@@ -45,8 +50,9 @@ struct dm_dev_weights {
   float* b32[2][3];        // fp32 bias    [400]
   float* cls_w;            // [200][2]
   float* cls_b;            // [2]
-  __nv_bfloat16* wtc[2][3];  // tensor-core images, one CTA per tile (see dm_lstm_tc.cu)
-  __nv_bfloat16* wtc2[2][3]; // tensor-core images split by CTA of a pair (cta_group::2)
+  // tensor-core images (see dm_lstm_tc.cu), 16-bit words; first index = operand format (0 bf16, 1 fp16)
+  uint16_t* wtc[2][2][3];    // one CTA per tile
+  uint16_t* wtc2[2][2][3];   // split by CTA of a pair (cta_group::2)
   float* cls_d;            // [2][100] cls_w[:,1]-cls_w[:,0] per direction
   float cls_db;            // cls_b[1]-cls_b[0]
 };
@@ -68,7 +74,7 @@ struct dm_dev_batch {
   int32_t *status = nullptr;      // [n_reads]
   int32_t *align_status = nullptr;  // [n_reads] verdict of the CIGAR walk (dm_align_upload), merged into status on fetch
   float *feat = nullptr;          // [n_frows+21][8] fp32 feature rows (+21 all-zero rows)
-  __nv_bfloat16* feat_tc = nullptr;  // [n_frows+21][16] bf16 hi/lo rows for the tensor-core path
+  uint16_t* feat_tc = nullptr;    // [n_frows+21][16] 16-bit hi/lo rows for the tensor-core path (bf16 or fp16, ctx->tc_f16)
   float *p1 = nullptr;            // [n_windows_padded]
   uint8_t *pred = nullptr;        // [n_windows_padded]
   // capacity bookkeeping (buffers are grown, never shrunk)
@@ -102,6 +108,9 @@ struct dm_ctx {
   uint8_t* motif = nullptr;                      // same indexing: 1 = motif (CpG) site, for the cluster second pass
   int64_t n_cells = 0;
   char base = 'C';
+  int* overflow_d = nullptr;                     // set by k_accumulate when a coverage counter reaches DM_CELL_MASK
+  void* nccl_comm = nullptr; int nccl_rank = 0, nccl_ranks = 0;   // dm_reduce_comm's communicator (kept across calls)
+  float reduce_ms = 0.f;                         // device time of the last dm_reduce / dm_reduce_comm exchange
   // scratch
   void* scratch = nullptr; size_t scratch_bytes = 0;
   void* hbuf = nullptr; size_t hbuf_bytes = 0;   // inter-layer hidden states (tensor-core path)
@@ -111,6 +120,7 @@ struct dm_ctx {
   float lstm_ms = 0.f, total_ms = 0.f;
   bool fp32_attr_set = false, tc_attr_set = false;
   bool tc_pair = true;            // CTA-pair (cta_group::2) variant of the tensor-core kernel
+  bool tc_f16 = false;            // operand format of the tensor-core path: fp16 (DM_F16) instead of bf16
   std::string err;
 };
 
@@ -134,6 +144,10 @@ int dm_signal_event_stats(dm_ctx* ctx, int32_t n_reads, const int64_t* raw_off, 
 int dm_launch_prepare(dm_ctx* ctx);                       // dm_features.cu
 int dm_launch_build_windows(dm_ctx* ctx, float* out_d);   // dm_features.cu
 int dm_launch_accumulate(dm_ctx* ctx);                    // dm_hist.cu
+int dm_check_overflow(dm_ctx* ctx);                       // dm_hist.cu: DM_ERR_OVERFLOW if a counter hit its limit (syncs the stream)
+int dm_hist_max_cov(dm_ctx* ctx, unsigned long long* max_cov);   // dm_hist.cu
+int dm_hist_normalise_flags(dm_ctx* ctx);                 // dm_hist.cu: key-created field back to 0/1 after a sum
+void dm_reduce_release(dm_ctx* ctx);                      // dm_reduce.cu: destroys the context's communicator
 int dm_launch_mask_rejected(dm_ctx* ctx);                 // dm_hist.cu
 struct dm_cluster_result {                                 // output of the cluster second pass (dm_cluster.cu)
   std::vector<int64_t> pos;
@@ -151,14 +165,14 @@ int dm_hist_compact(dm_ctx* ctx, int32_t contig, int8_t strand, std::vector<int6
 // BiLSTM over the uploaded batch's feature table -> b.p1 / b.pred
 int dm_launch_lstm_fp32(dm_ctx* ctx, const float* feat, const int32_t* win_frow, int64_t n_windows,
                         float* p1, uint8_t* pred);        // dm_lstm_fp32.cu
-int dm_launch_lstm_tc(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow,
+int dm_launch_lstm_tc(dm_ctx* ctx, const uint16_t* feat_tc, const int32_t* win_frow,
                       int64_t n_windows, float* p1, uint8_t* pred);   // dm_lstm_tc.cu
 int dm_tc_selftest(dm_ctx* ctx, int n, int k, float* max_err);       // dm_lstm_tc.cu
-int dm_tc_debug(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_windows,
+int dm_tc_debug(dm_ctx* ctx, const uint16_t* feat_tc, const int32_t* win_frow, int64_t n_windows,
                 float* p1, uint8_t* pred, int max_steps, unsigned char* dump_host, int64_t dump_cap);
 // window-level entry: explicit [n,21,7] windows -> feature rows (21 per window)
 int dm_launch_windows_to_rows(dm_ctx* ctx, const float* X_d, int64_t n, float* feat,
-                              __nv_bfloat16* feat_tc, int32_t* win_frow);   // dm_features.cu
+                              uint16_t* feat_tc, int32_t* win_frow);   // dm_features.cu
 
 // result buffers are padded to whole CTA pairs (2 x 128 windows)
 static inline int64_t dm_pad_windows(int64_t n) { return (n + 2 * DM_TILE_M - 1) / (2 * DM_TILE_M) * (2 * DM_TILE_M); }

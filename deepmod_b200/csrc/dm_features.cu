@@ -11,6 +11,8 @@
 // the BiLSTM kernels read rows through win_frow[] (first row of each window).
 #include "dm_common.cuh"
 
+#include <cuda_fp16.h>
+
 namespace {
 
 constexpr int SCAN_BLOCK = 256;
@@ -145,13 +147,37 @@ __global__ void k_map_columns(int n_reads, int64_t n_cols, const int64_t* __rest
   }
 }
 
+// 16-bit hi/lo split row for the tensor-core path, in the K order of the layer-0 weight image:
+// [A C G T mean_hi stdv_hi len_hi len_lo | 1 1 mean_lo stdv_lo | pad]; bf16 or fp16 operands
+__device__ __forceinline__ void tc_split_row(const float (&f)[8], uint16_t* dst, bool f16) {
+  auto rn = [f16](float x) -> uint16_t {
+    return f16 ? __half_as_ushort(__float2half_rn(x)) : __bfloat16_as_ushort(__float2bfloat16(x));
+  };
+  auto back = [f16](uint16_t b) -> float {
+    return f16 ? __half2float(__ushort_as_half(b)) : __bfloat162float(__ushort_as_bfloat16(b));
+  };
+  __align__(16) uint16_t h[16];
+  for (int i = 0; i < 4; ++i) h[i] = rn(f[i]);
+  const uint16_t mh = rn(f[4]), sh = rn(f[5]), lh = rn(f[6]);
+  h[4] = mh; h[5] = sh; h[6] = lh;
+  h[7] = rn(f[6] - back(lh));
+  h[8] = h[9] = rn(1.f);
+  h[10] = rn(f[4] - back(mh));
+  h[11] = rn(f[5] - back(sh));
+  h[12] = h[13] = h[14] = h[15] = 0;
+  uint4* ot = reinterpret_cast<uint4*>(dst);
+  const uint4* hs = reinterpret_cast<const uint4*>(h);
+  ot[0] = hs[0];
+  ot[1] = hs[1];
+}
+
 // One thread per feature row: ie = start_clip - 10 + j walks the +-10 flank (:855-900).
 __global__ void k_feature_rows(int n_reads, int64_t n_frows, const int64_t* __restrict__ win_off,
                                const int64_t* __restrict__ ev_off, const float* __restrict__ ev_mean,
                                const float* __restrict__ ev_stdv, const float* __restrict__ ev_len,
                                const int32_t* __restrict__ start_clip, const int32_t* __restrict__ end_clip,
                                const int64_t* __restrict__ win_col, const uint8_t* __restrict__ refbase,
-                               float* __restrict__ feat, __nv_bfloat16* __restrict__ feat_tc) {
+                               float* __restrict__ feat, uint16_t* __restrict__ feat_tc, bool f16) {
   int64_t fr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (fr >= n_frows + DM_WINDOW) return;       // rows >= n_frows: the shared all-zero window
   float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -186,23 +212,7 @@ __global__ void k_feature_rows(int n_reads, int64_t n_frows, const int64_t* __re
   float4* o = reinterpret_cast<float4*>(feat + fr * DM_FEAT_STRIDE);
   o[0] = make_float4(f[0], f[1], f[2], f[3]);
   o[1] = make_float4(f[4], f[5], f[6], 0.f);
-  if (feat_tc != nullptr) {
-    // bf16 hi/lo split rows for the tensor-core path, in the K order of the layer-0
-    // weight image: [A C G T mean_hi stdv_hi len_hi len_lo | 1 1 mean_lo stdv_lo | pad]
-    __nv_bfloat16 h[16];
-    for (int i = 0; i < 4; ++i) h[i] = __float2bfloat16(f[i]);
-    __nv_bfloat16 mh = __float2bfloat16(f[4]), sh = __float2bfloat16(f[5]), lh = __float2bfloat16(f[6]);
-    h[4] = mh; h[5] = sh; h[6] = lh;
-    h[7] = __float2bfloat16(f[6] - __bfloat162float(lh));
-    h[8] = __float2bfloat16(1.f); h[9] = __float2bfloat16(1.f);
-    h[10] = __float2bfloat16(f[4] - __bfloat162float(mh));
-    h[11] = __float2bfloat16(f[5] - __bfloat162float(sh));
-    h[12] = h[13] = h[14] = h[15] = __float2bfloat16(0.f);
-    uint4* ot = reinterpret_cast<uint4*>(feat_tc + fr * 16);
-    const uint4* hs = reinterpret_cast<const uint4*>(h);
-    ot[0] = hs[0];
-    ot[1] = hs[1];
-  }
+  if (feat_tc != nullptr) tc_split_row(f, feat_tc + fr * 16, f16);
 }
 
 // win_frow[w] = first feature row of window w; padded tail -> the zero row
@@ -217,7 +227,7 @@ __global__ void k_window_rows(int n_reads, int64_t n_windows, int64_t n_padded, 
 
 // explicit windows [n,21,7] (the b1 seam) -> 21 feature rows each
 __global__ void k_windows_to_rows(const float* __restrict__ X, int64_t n, int64_t n_padded,
-                                  float* __restrict__ feat, __nv_bfloat16* __restrict__ feat_tc,
+                                  float* __restrict__ feat, uint16_t* __restrict__ feat_tc, bool f16,
                                   int32_t* __restrict__ win_frow) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // row index
   int64_t n_rows = n * DM_WINDOW;
@@ -229,23 +239,8 @@ __global__ void k_windows_to_rows(const float* __restrict__ X, int64_t n, int64_
   float4* o = reinterpret_cast<float4*>(feat + i * DM_FEAT_STRIDE);
   o[0] = make_float4(f[0], f[1], f[2], f[3]);
   o[1] = make_float4(f[4], f[5], f[6], 0.f);
-  if (feat_tc != nullptr) {
-    // general inputs: split every feature hi/lo is not possible in 12 slots, so the
-    // four base columns are taken as-is (they are 0/1 in every reference window)
-    __nv_bfloat16 h[16];
-    for (int k = 0; k < 4; ++k) h[k] = __float2bfloat16(f[k]);
-    __nv_bfloat16 mh = __float2bfloat16(f[4]), sh = __float2bfloat16(f[5]), lh = __float2bfloat16(f[6]);
-    h[4] = mh; h[5] = sh; h[6] = lh;
-    h[7] = __float2bfloat16(f[6] - __bfloat162float(lh));
-    h[8] = __float2bfloat16(1.f); h[9] = __float2bfloat16(1.f);
-    h[10] = __float2bfloat16(f[4] - __bfloat162float(mh));
-    h[11] = __float2bfloat16(f[5] - __bfloat162float(sh));
-    h[12] = h[13] = h[14] = h[15] = __float2bfloat16(0.f);
-    uint4* ot = reinterpret_cast<uint4*>(feat_tc + i * 16);
-    const uint4* hs = reinterpret_cast<const uint4*>(h);
-    ot[0] = hs[0];
-    ot[1] = hs[1];
-  }
+  // (general inputs: the four base columns are taken as-is, they are 0/1 in every reference window)
+  if (feat_tc != nullptr) tc_split_row(f, feat_tc + i * 16, f16);
 }
 
 // coalesced gather: thread per output float of the [n_windows,21,7] tensor
@@ -306,7 +301,7 @@ int dm_launch_prepare(dm_ctx* ctx) {
   }
   k_feature_rows<<<blocks_for(b.n_frows + DM_WINDOW, 256), 256, 0, s>>>(
       b.n_reads, b.n_frows, b.win_off, b.ev_off, b.ev_mean, b.ev_stdv, b.ev_len, b.start_clip,
-      b.end_clip, b.win_col, b.col_refbase, b.feat, b.feat_tc);
+      b.end_clip, b.win_col, b.col_refbase, b.feat, b.feat_tc, ctx->tc_f16);
   const int64_t n_pad = dm_pad_windows(b.n_windows);
   if (n_pad > 0) {
     k_window_rows<<<blocks_for(n_pad, 256), 256, 0, s>>>(b.n_reads, b.n_windows, n_pad, b.n_frows,
@@ -329,11 +324,11 @@ int dm_launch_build_windows(dm_ctx* ctx, float* out_d) {
 }
 
 int dm_launch_windows_to_rows(dm_ctx* ctx, const float* X_d, int64_t n, float* feat,
-                              __nv_bfloat16* feat_tc, int32_t* win_frow) {
+                              uint16_t* feat_tc, int32_t* win_frow) {
   int64_t n_pad = dm_pad_windows(n);
   int64_t threads = (n + 1) * DM_WINDOW;
   if (threads < n_pad) threads = n_pad;
-  k_windows_to_rows<<<blocks_for(threads, 256), 256, 0, ctx->stream>>>(X_d, n, n_pad, feat, feat_tc, win_frow);
+  k_windows_to_rows<<<blocks_for(threads, 256), 256, 0, ctx->stream>>>(X_d, n, n_pad, feat, feat_tc, ctx->tc_f16, win_frow);
   ctx->launches += 1;
   DM_CUDA(ctx, cudaGetLastError());
   return DM_OK;

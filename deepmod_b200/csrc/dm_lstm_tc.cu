@@ -17,9 +17,12 @@
 //  * weights (bf16, 0.5 folded into the sigmoid gates, forget bias folded into the bias)
 //    stream from L2 through a 4-stage shared-memory ring with cp.async.bulk + mbarriers,
 //    pre-arranged on the host in the exact UMMA canonical (no-swizzle, K-major) layout;
-//  * the epilogue (20 warps) reads 16 TMEM columns = 4 units per thread and chunk, applies
-//    sigmoid(x) = 0.5*tanh(x/2)+0.5 and tanh with one MUFU each, keeps the cell state in
-//    packed fp16 registers and writes h back as bf16 straight into the next A operand.
+//  * the epilogue (20 warps) reads 16 TMEM columns = 4 units per thread and chunk, packs the gate
+//    pre-activations of TWO units into f16x2 and applies sigmoid(x) = 0.5*tanh(x/2)+0.5 and tanh
+//    with ONE tanh.approx.f16x2 per pair (2.5 MUFU per unit instead of 5), does the cell update in
+//    packed half2 FMAs (cell state in packed fp16 registers) and writes 2h straight into the next
+//    A operand (the factor 0.5 of h = 0.5*(tanh(c)*tanh(o/2) + tanh(c)) is folded into the weights);
+//  * operands are fp16 (DM_F16: h needs no conversion at all) or bf16 (DM_BF16), fp32 accumulate.
 #include "dm_common.cuh"
 
 #include <cuda_fp16.h>
@@ -58,11 +61,11 @@ __host__ __device__ constexpr int tc_unit0(int j, int s);
 #ifndef TC_UNIWARP
 #define TC_UNIWARP 1       // warp index through a shuffle (provably warp-uniform for the compiler)
 #endif
-#ifndef TC_EARLYTEST
-#define TC_EARLYTEST 0     // 1: probe the next chunk's barrier (non-blocking) before the cell update
-#endif
-#ifndef TC_LDSPLIT
-#define TC_LDSPLIT 1       // 1: the next chunk's accumulator comes in two x8 loads, the first one half a chunk earlier
+#ifndef TC_EARLYLD
+#define TC_EARLYLD 0       // when the next chunk's accumulator load is issued (its 16 registers are free as soon as the
+                           // gate columns are packed to f16x2): 1 = right after the packing (waits for its barrier
+                           // there), 2 = there if a non-blocking probe finds it ready, else after the cell update,
+                           // 0 = always after the cell update
 #endif
 #ifndef TC_T0TRIM
 #define TC_T0TRIM 1        // 1: at t == 0 (h_prev == 0) the MMAs over the own hidden tile are not issued, and a direction
@@ -258,15 +261,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | (1ull << 46);
 }
-// instruction descriptor: D = f32, A = B = bf16, both K-major, dense
-__host__ __device__ constexpr uint32_t umma_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// instruction descriptor: D = f32, A = B = bf16 (format 1) or fp16 (format 0), both K-major, dense
+__host__ __device__ constexpr uint32_t umma_idesc(int m, int n, bool f16 = false) {
+  return (1u << 4) | (f16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float tanh_mufu(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
+// one MUFU, two results
+__device__ __forceinline__ __half2 tanh2_mufu(__half2 x) {
+  uint32_t y;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(*reinterpret_cast<const uint32_t*>(&x)));
+  return *reinterpret_cast<__half2*>(&y);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
@@ -306,9 +310,9 @@ __device__ __forceinline__ int tau_row(int dir, int tau) { return dir == 0 ? tau
 // drained relay (peer CTA); 22 TMEM allocator / hidden-state-written relay (peer); 23 stage-landed
 // relay (peer).  The relays exist because a cluster-scope release-arrive costs ~1000 cycles: the
 // peer's 20 epilogue warps arrive on cheap CTA-local barriers and ONE thread forwards each phase.
-template <bool PAIR, bool DBG>
+template <bool PAIR, bool DBG, bool F16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__ win_frow, dm_dev_weights w,
+k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_frow, dm_dev_weights w,
           float* __restrict__ p1_out, uint8_t* __restrict__ pred_out, int n_tiles, int max_steps,
           unsigned char* __restrict__ dbg) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -444,7 +448,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
     if (lane == 0 && !dbg_noload) {
       uint32_t slot = 0, use = 0;
       FOR_EACH_STEP({
-        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(PAIR ? w.wtc2[dir][l] : w.wtc[dir][l]);
+        const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(PAIR ? w.wtc2[F16][dir][l] : w.wtc[F16][dir][l]);
         const int ncols = l == 0 ? 14 : 26;
         const uint32_t bytes = ncols * G::BCOL;
         for (int j = 0; j < TC_NCHUNK; ++j) {
@@ -497,7 +501,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
     // `if (lane == 0)` makes the compiler broadcast every operand of every MMA through a waterfall loop).
     {
       const uint32_t mine = warp == W_MMA ? 0u : 1u;
-      constexpr uint32_t idesc = umma_idesc(PAIR ? 256 : 128, TC_CHUNK_N);
+      constexpr uint32_t idesc = umma_idesc(PAIR ? 256 : 128, TC_CHUNK_N, F16);
       constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);         // SBO = 128 B, descriptor version 1
       constexpr uint32_t b_step = (2 * G::BCOL) >> 4;                // two K core columns per MMA
       uint32_t slot = 0, use = 0, tslot = 0, tuse = 0, c = 0;
@@ -639,7 +643,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             if (sgrp == 4)   // (1, 1, mean_lo, stdv_lo) of the next time index ride in h0's extras
               lows = *reinterpret_cast<const uint2*>(feat_tc + ((int64_t)FROW(row) + tau_row(dir, t + 1 <= 10 ? t + 1 : 10)) * 16 + 8);
           } else if (l == 1) {
-            lows = make_uint2(0x3F803F80u, 0u);     // (1, 1, 0, 0): bias carriers for layer 2
+            lows = make_uint2(F16 ? 0x3C003C00u : 0x3F803F80u, 0u);     // (1, 1, 0, 0): bias carriers for layer 2
           }
           const uint32_t htile = l == 0 ? OFF_H0 + (t & 1) * TC_HTILE : l == 1 ? OFF_H1 + (t & 1) * TC_HTILE : OFF_H2;
           // h2 is single-buffered and its old value is an operand of ALL five chunks of this very
@@ -668,20 +672,15 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             tc_fence_after();
             tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
           }
-          // h of chunk jj (units tc_unit0(jj, sgrp) ..+3): classifier partial, bf16 pack, store into the next A operand.
+          // 2h of chunk jj (units tc_unit0(jj, sgrp) ..+3) as two packed 16-bit pairs: store into the next A operand.
           // With TC_UNITMAP two consecutive chunks fill one 16-byte row segment (8 units): the first half waits in two
           // registers and the pair leaves as ONE 16-byte store per lane (32 lanes x 16 B contiguous: no bank conflict).
           // Even column groups pair chunks (0,1), (2,3); odd ones start mid-segment and pair (1,2), (3,4).
           uint32_t ph0 = 0, ph1 = 0;
-          auto emit = [&](int jj, const float (&hn)[4]) {
+          auto emit = [&](int jj, const uint32_t h01, const uint32_t h23) {
             const int u0 = tc_unit0(jj, sgrp);
-            if (l == 2 && t == 10) {
-              const float* cw = s_cls + dir * DM_HIDDEN + u0;
-              cls_acc += hn[0] * cw[0] + hn[1] * cw[1] + hn[2] * cw[2] + hn[3] * cw[3];
-            }
             // core column u0/8, byte (u0%8)*2 of the row's 16 B
             unsigned char* dst = smem + htile + (u0 >> 3) * TC_ACOL + row_off + (u0 & 7) * 2;
-            const uint32_t h01 = pack_bf16(hn[0], hn[1]), h23 = pack_bf16(hn[2], hn[3]);
             const bool odd = (sgrp & 1) != 0;
             const bool pair_lo = TC_UNITMAP && (odd ? (jj == 1 || jj == 3) : (jj == 0 || jj == 2));
             const bool pair_hi = TC_UNITMAP && (odd ? (jj == 2 || jj == 4) : (jj == 1 || jj == 3));
@@ -707,6 +706,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
               *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
             }
           };
+          const __half2 half2_half = __floats2half2_rn(0.5f, 0.5f);
 #pragma unroll
           for (int j = 0; j < TC_NCHUNK; ++j) {
             if (stamp) TS(ts0 + g * 16 + 3 * j);
@@ -721,65 +721,65 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             if (lane == 0) mbar_arrive(bar0 + 8 * (BAR_TEMPTY + tslot));      // CTA-local; the peer's relay forwards
             if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
             if (stamp) TS(ts0 + g * 16 + 3 * j + 2);
-            // early non-blocking probe of the next chunk's barrier: its latency hides behind the cell update
-            const bool nxt = TC_PREFETCH && (j + 1 < TC_NCHUNK || cross);       // (tslot, tuse) now name the next chunk
-            const bool rdy = TC_EARLYTEST && nxt && __all_sync(0xffffffffu, mbar_test(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1));
-            // cell update of chunk j
-            float cn[4] = {0.f, 0.f, 0.f, 0.f}, so[4] = {0.f, 0.f, 0.f, 0.f};
+            // gate pre-activations of units (0,1) and (2,3) as f16x2 (low half = the even unit): one cvt per pair
+            // and gate, and from here on v is dead
+            __half2 gi[2], gj[2], gf[2], go[2];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+              gi[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 0]), __uint_as_float(v[8 * p + 4]));
+              gj[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 1]), __uint_as_float(v[8 * p + 5]));
+              gf[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 2]), __uint_as_float(v[8 * p + 6]));
+              go[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 3]), __uint_as_float(v[8 * p + 7]));
+            }
+            // the next chunk's accumulator load overlaps this chunk's cell update ((tslot, tuse) now name the next chunk)
+            const bool nxt = TC_PREFETCH && (j + 1 < TC_NCHUNK || cross);
+            bool loaded = false;
+            if (nxt && TC_EARLYLD) {
+              bool rdy = true;
+              if (TC_EARLYLD == 2) rdy = __all_sync(0xffffffffu, mbar_test(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1));
+              else mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+              if (rdy) {
+                tc_fence_after();
+                tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
+                loaded = true;
+              }
+            }
+            // cell update of chunk j:  c' = c * sig(f) + sig(i) * tanh(j),  2h = tanh(c') * tanh(o/2) + tanh(c')
+            uint32_t hp[2] = {0u, 0u};
             if (!dbg_nomath) {
 #pragma unroll
               for (int p = 0; p < 2; ++p) {
-                const float2 cp = __half22float2(cst[l][j][p]);
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                  const int u = 2 * p + k;
-                  const float ti = tanh_mufu(__uint_as_float(v[4 * u + 0]));
-                  const float tj = tanh_mufu(__uint_as_float(v[4 * u + 1]));
-                  const float to = tanh_mufu(__uint_as_float(v[4 * u + 3]));
-                  const float si = fmaf(ti, 0.5f, 0.5f);
-                  so[u] = fmaf(to, 0.5f, 0.5f);
-                  if (TC_T0SKIP && t == 0) {            // c_prev == 0: the forget gate cannot matter
-                    cn[u] = si * tj;
-                  } else {
-                    const float sf = fmaf(tanh_mufu(__uint_as_float(v[4 * u + 2])), 0.5f, 0.5f);
-                    cn[u] = fmaf(k == 0 ? cp.x : cp.y, sf, si * tj);
-                  }
-                  if (TC_LDSPLIT == 2 && nxt && u < 3) {
-                    // unit u has read its four gate columns: the next chunk's unit u follows at once
-                    if (u == 0) {
-                      if (!rdy) mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
-                      tc_fence_after();
-                    }
-                    tc_ld4(t_lane + tslot * TC_CHUNK_N + 4 * u, v + 4 * u);
-                  }
+                const __half2 ti = tanh2_mufu(gi[p]), tj = tanh2_mufu(gj[p]), to = tanh2_mufu(go[p]);
+                const __half2 y = __hmul2(__hfma2(ti, half2_half, half2_half), tj);
+                __half2 cn;
+                if (TC_T0SKIP && t == 0) {            // c_prev == 0: the forget gate cannot matter
+                  cn = y;
+                } else {
+                  const __half2 cp = cst[l][j][p];
+                  cn = __hfma2(__hfma2(cp, tanh2_mufu(gf[p]), cp), half2_half, y);
                 }
-                cst[l][j][p] = __floats2half2_rn(cn[2 * p], cn[2 * p + 1]);
-                if (TC_LDSPLIT == 1 && p == 0 && nxt) {
-                  // units 0, 1 have read their half of v: the next chunk's first 8 columns start flying now
-                  if (!rdy) mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
-                  tc_fence_after();
-                  tc_ld8(t_lane + tslot * TC_CHUNK_N, v);
+                cst[l][j][p] = cn;
+                const __half2 tc = tanh2_mufu(cn);
+                const __half2 h2 = __hfma2(tc, to, tc);
+                if (l == 2 && t == 10) {
+                  const float2 hf = __half22float2(h2);
+                  const float* cw = s_cls + dir * DM_HIDDEN + tc_unit0(j, sgrp) + 2 * p;
+                  cls_acc += hf.x * cw[0] + hf.y * cw[1];
+                }
+                if (F16) {
+                  hp[p] = *reinterpret_cast<const uint32_t*>(&h2);
+                } else {
+                  const float2 hf = __half22float2(h2);
+                  hp[p] = pack_bf16(hf.x, hf.y);
                 }
               }
             }
-            if (nxt) {
-              // v is dead: the next chunk's barrier probe and TMEM load overlap this chunk's packing and stores
-              if (TC_LDSPLIT == 1 && !dbg_nomath) {
-                tc_ld8(t_lane + tslot * TC_CHUNK_N + 8, v + 8);
-              } else if (TC_LDSPLIT == 2 && !dbg_nomath) {
-                tc_ld4(t_lane + tslot * TC_CHUNK_N + 12, v + 12);
-              } else {
-                if (!rdy) mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
-                tc_fence_after();
-                tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
-              }
+            if (nxt && !loaded) {
+              mbar_wait(bar0 + 8 * (BAR_TFULL + tslot), tuse & 1);
+              tc_fence_after();
+              tc_ld16(t_lane + tslot * TC_CHUNK_N, v);
             }
-            {
-              float hn[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) hn[u] = dbg_nomath ? 0.f : tanh_mufu(cn[u]) * so[u];
-              emit(j, hn);
-            }
+            emit(j, hp[0], hp[1]);
           }
           if (l == 0 && sgrp == 0 && t + 2 <= 10)
             *reinterpret_cast<uint4*>(smem + OFF_X + (t & 1) * TC_ACOL + row_off) = xnext;
@@ -809,7 +809,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
             if (sgrp == 0) {
               float dl = w.cls_db;
 #pragma unroll
-              for (int s5 = 0; s5 < 5; ++s5) { dl += s_part[s5 * 128 + row]; s_part[s5 * 128 + row] = 0.f; }
+              for (int s5 = 0; s5 < 5; ++s5) { dl += 0.5f * s_part[s5 * 128 + row]; s_part[s5 * 128 + row] = 0.f; }   // partials hold 2h
               if (p1_out) p1_out[win0 + row] = 1.0f / (1.0f + __expf(-dl));
               if (pred_out) pred_out[win0 + row] = dl > 0.f ? 1 : 0;
             }
@@ -836,7 +836,7 @@ k_lstm_tc(const __nv_bfloat16* __restrict__ feat_tc, const int32_t* __restrict__
               if (sgrp == 0) {
                 float dl = w.cls_db;
 #pragma unroll
-                for (int s = 0; s < 5; ++s) dl += s_part[s * 128 + row];
+                for (int s = 0; s < 5; ++s) dl += 0.5f * s_part[s * 128 + row];      // the partials hold 2h
                 // softmax over two classes: p1 = 1/(1+exp(l0-l1)); argmax picks class 1 iff l1 > l0
                 if (p1_out) p1_out[win0 + row] = 1.0f / (1.0f + __expf(-dl));
                 if (pred_out) pred_out[win0 + row] = dl > 0.f ? 1 : 0;
@@ -942,6 +942,9 @@ float h_bf16f(uint16_t b) {
   memcpy(&f, &u, 4);
   return f;
 }
+// 16-bit operand formats of the tensor-core path (host side): round to nearest even, and back
+uint16_t h_rn16(float f, bool f16) { return f16 ? __half_as_ushort(__float2half_rn(f)) : h_bf16(f); }
+float h_rn16f(uint16_t b, bool f16) { return f16 ? __half2float(__ushort_as_half(b)) : h_bf16f(b); }
 
 }  // namespace
 
@@ -952,10 +955,13 @@ float h_bf16f(uint16_t b) {
 //   layer 1,2: cols 0..12 = tile of the layer below (100/101 carry this layer's bias),
 //            cols 13..25 = own hidden tile (extras unused).
 // The sigmoid gates (i, f, o) are pre-scaled by 0.5 because the epilogue evaluates
-// sigmoid(x) = 0.5*tanh(x/2)+0.5; forget_bias = 1.0 (BasicLSTMCell) is folded into the bias.
+// sigmoid(x) = 0.5*tanh(x/2)+0.5; forget_bias = 1.0 (BasicLSTMCell) is folded into the bias.  Every row that
+// multiplies a hidden state carries another 0.5: the epilogue stores 2h = tanh(c)*tanh(o/2) + tanh(c).
+// (Both factors are powers of two: the rounded weights are exactly the scaled roundings.)
 // pair = true: [chunk j][cta r][core column kc][n 40][8 k], CTA r owning gate columns n = 40 r .. 40 r + 39
 // of the chunk (tcgen05.mma.cta_group::2 takes the first half of B's N rows from the even CTA).
-void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool pair, std::vector<uint16_t>& img) {
+// f16: fp16 instead of bf16 words.
+void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool pair, bool f16, std::vector<uint16_t>& img) {
   const int ncols = layer == 0 ? 14 : 26;
   img.assign((size_t)TC_NCHUNK * ncols * TC_CHUNK_N * 8, 0);
   for (int j = 0; j < TC_NCHUNK; ++j)
@@ -964,17 +970,18 @@ void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool 
         const int unit = tc_unit0(j, n / 16) + (n / 4) % 4, gate = n % 4, col = gate * DM_HIDDEN + unit;
         const float scale = gate == 1 ? 1.0f : 0.5f;
         const float bsc = (bias[col] + (gate == 2 ? 1.0f : 0.0f)) * scale;
-        const uint16_t bhi = h_bf16(bsc), blo = h_bf16(bsc - h_bf16f(bhi));
+        const uint16_t bhi = h_rn16(bsc, f16), blo = h_rn16(bsc - h_rn16f(bhi, f16), f16);
         for (int e = 0; e < 8; ++e) {
           uint16_t val = 0;
-          auto wref = [&](int r) { return h_bf16(kernel[(size_t)r * DM_GATES + col] * scale); };
+          auto wref = [&](int r) { return h_rn16(kernel[(size_t)r * DM_GATES + col] * scale, f16); };          // input rows
+          auto href = [&](int r) { return h_rn16(kernel[(size_t)r * DM_GATES + col] * scale * 0.5f, f16); };   // rows against 2h
           if (layer == 0) {
             if (kc == 0) {
               static const int xr[8] = {0, 1, 2, 3, 4, 5, 6, 6};
               val = wref(xr[e]);
             } else {
               const int kk = (kc - 1) * 8 + e;
-              if (kk < DM_HIDDEN) val = wref(DM_FNUM + kk);
+              if (kk < DM_HIDDEN) val = href(DM_FNUM + kk);
               else if (kk == 100) val = bhi;
               else if (kk == 101) val = blo;
               else if (kk == 102) val = wref(4);
@@ -983,12 +990,12 @@ void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool 
           } else {
             if (kc < TC_HCOLS) {
               const int kk = kc * 8 + e;
-              if (kk < DM_HIDDEN) val = wref(kk);
+              if (kk < DM_HIDDEN) val = href(kk);
               else if (kk == 100) val = bhi;
               else if (kk == 101) val = blo;
             } else {
               const int kk = (kc - TC_HCOLS) * 8 + e;
-              if (kk < DM_HIDDEN) val = wref(DM_HIDDEN + kk);
+              if (kk < DM_HIDDEN) val = href(DM_HIDDEN + kk);
             }
           }
           if (pair) img[((((size_t)j * 2 + n / 40) * ncols + kc) * 40 + n % 40) * 8 + e] = val;
@@ -997,51 +1004,52 @@ void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool 
       }
 }
 
+using tc_kernel_t = void (*)(const uint16_t*, const int32_t*, dm_dev_weights, float*, uint8_t*, int, int, unsigned char*);
+static tc_kernel_t tc_kernel(bool pair, bool dbg, bool f16) {
+  static const tc_kernel_t tab[8] = {
+      k_lstm_tc<false, false, false>, k_lstm_tc<false, false, true>, k_lstm_tc<false, true, false>, k_lstm_tc<false, true, true>,
+      k_lstm_tc<true, false, false>,  k_lstm_tc<true, false, true>,  k_lstm_tc<true, true, false>,  k_lstm_tc<true, true, true>};
+  return tab[(pair ? 4 : 0) + (dbg ? 2 : 0) + (f16 ? 1 : 0)];
+}
+
 static int tc_prepare(dm_ctx* ctx) {
   if (!ctx->tc_attr_set) {
-    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
-    DM_CUDA(ctx, cudaFuncSetAttribute(k_lstm_tc<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
+    for (int i = 0; i < 8; ++i)
+      DM_CUDA(ctx, cudaFuncSetAttribute(reinterpret_cast<const void*>(tc_kernel((i & 4) != 0, (i & 2) != 0, (i & 1) != 0)),
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM));
     DM_CUDA(ctx, cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     ctx->tc_attr_set = true;
   }
   return DM_OK;
 }
 
-static int tc_launch(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_pad, float* p1,
+static int tc_launch(dm_ctx* ctx, const uint16_t* feat_tc, const int32_t* win_frow, int64_t n_pad, float* p1,
                      uint8_t* pred, int max_steps, unsigned char* dbg) {
   const unsigned tiles = (unsigned)(n_pad / DM_TILE_M);       // n_pad is a multiple of 256: an even number of tiles
   // persistent CTAs: one per SM (an even number, so that pairs stay whole); the debug entry runs one tile per CTA
   unsigned grid = (unsigned)(ctx->sm_count & ~1);
   if (dbg != nullptr || max_steps != 2 * TC_STEPS_PER_DIR || grid > tiles) grid = tiles;
   const bool debug = dbg != nullptr || max_steps != 2 * TC_STEPS_PER_DIR;
-  if (ctx->tc_pair) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = TC_SMEM;
-    cfg.stream = ctx->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (debug) DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstm_tc<true, true>, feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg));
-    else DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, k_lstm_tc<true, false>, feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg));
-  } else if (debug) {
-    k_lstm_tc<false, true><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg);
-  } else {
-    k_lstm_tc<false, false><<<grid, TC_THREADS, TC_SMEM, ctx->stream>>>(feat_tc, win_frow, ctx->w, p1, pred, (int)tiles, max_steps, dbg);
-  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = TC_SMEM;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ctx->tc_pair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DM_CUDA(ctx, cudaLaunchKernelEx(&cfg, tc_kernel(ctx->tc_pair, debug, ctx->tc_f16), feat_tc, win_frow, ctx->w, p1, pred,
+                                  (int)tiles, max_steps, dbg));
   ctx->launches += 1;
   DM_CUDA(ctx, cudaGetLastError());
   return DM_OK;
 }
 
-int dm_launch_lstm_tc(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_windows,
+int dm_launch_lstm_tc(dm_ctx* ctx, const uint16_t* feat_tc, const int32_t* win_frow, int64_t n_windows,
                       float* p1, uint8_t* pred) {
   const int64_t n_pad = dm_pad_windows(n_windows);
   if (n_pad == 0) return DM_OK;
@@ -1052,7 +1060,7 @@ int dm_launch_lstm_tc(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* 
 
 // debug: run the first `max_steps` cell-steps and return tile 0's shared-memory operand region
 // (x columns + the five hidden tiles, OFF_W bytes)
-int dm_tc_debug(dm_ctx* ctx, const __nv_bfloat16* feat_tc, const int32_t* win_frow, int64_t n_windows, float* p1,
+int dm_tc_debug(dm_ctx* ctx, const uint16_t* feat_tc, const int32_t* win_frow, int64_t n_windows, float* p1,
                 uint8_t* pred, int max_steps, unsigned char* dump_host, int64_t dump_cap) {
   const int64_t n_pad = dm_pad_windows(n_windows);
   if (n_pad == 0) return DM_OK;

@@ -49,9 +49,13 @@ k_signal_norm(int n_reads, const int64_t* __restrict__ raw_off, const int16_t* _
     const int64_t e0 = ev_off[r], e1 = ev_off[r + 1];
     ReadNorm res = {0.0, 1.0, 0.0, 0.0};
     if (e1 <= e0) { if (threadIdx.x == 0) out[r] = res; continue; }
-    const int64_t s0 = ev_start[e0], s1 = ev_start[e1 - 1] + ev_length[e1 - 1];
+    // mdata[mean_start:mean_end] (myDetect.py:266-270): numpy slicing clips the span to the read's raw array
+    const int64_t raw_len = raw_off[r + 1] - raw_off[r];
+    const int64_t s0 = min(max(ev_start[e0], (int64_t)0), raw_len);
+    const int64_t s1 = min(max(ev_start[e1 - 1] + ev_length[e1 - 1], s0), raw_len);
     const int16_t* x = raw + raw_off[r];
     const int64_t n = s1 - s0;
+    if (n <= 0) { if (threadIdx.x == 0) out[r] = res; continue; }       // (uniform per CTA) empty span: identity normalisation
     for (int i = threadIdx.x; i < NBIN; i += NT) hist[i] = 0;
     __syncthreads();
     for (int64_t i = s0 + threadIdx.x; i < s1; i += NT) atomicAdd(&hist[(int)x[i] + 32768], 1);

@@ -7,12 +7,15 @@ Mirrors ``bin/DeepMod_scripts/myDetect.py``:
 * ``detect_handler``             (:948-984)    one GPU context per process instead of one TF
   session per process; loops over packed read batches instead of FAST5 file batches;
 * ``sum_handler``                (:1028-1120)  reads the on-GPU accumulator instead of
-  re-reading per-read HDF5 detail files.
+  re-reading per-read HDF5 detail files (``--predDet 0`` still summarises stored per-read
+  predictions: ``deepmod_b200.predetail``).
 
 The reference's data parallelism is "file batches over processes + offline BED merge"
-(``docs/Usage.md:22-27``, ``DeepMod_tools/sum_chr_mod.py``); here reads shard over the GPUs of
-one box (one process per GPU, contiguous ranges balanced by mapped events) and the only
-exchange is one sum all-reduce of the packed (cov, mod, touched) cells at the end.
+(``myDetect.py:1160-1180``, ``docs/Usage.md:22-27``, ``DeepMod_tools/sum_chr_mod.py``); here the input FILES
+shard over the GPUs of one box (one process per GPU; if there are fewer files than GPUs, contiguous
+read ranges balanced by mapped events) and the only exchange is one sum all-reduce of the packed
+(cov, mod, key-created) cells at the end, inside the library (``dm_reduce_comm``, NCCL).  A loader
+thread reads, filters and packs file k+1 while the GPU works on file k.
 
 Inputs are *packed read batches* (``deepmod_b200.reads_io``): the per-read event tables and
 alignment columns that ``handle_record`` hands to ``get_Feature`` (:708-715).  FAST5 parsing
@@ -20,7 +23,9 @@ and the aligner call (:348-456) are outside this path.
 """
 import glob
 import os
+import queue
 import sys
+import threading
 import time
 
 import numpy as np
@@ -30,6 +35,8 @@ from . import capi, checkpoint, reads_io, sam, synth
 OUTPUT_DEBUG, OUTPUT_INFO, OUTPUT_WARNING, OUTPUT_ERROR = 0, 1, 2, 3     # myCom.py:5-8
 MAX_WINDOWS_PER_CALL = 16 * 1024 * 1024
 READS_GLOB = "*.dmreads.npz"
+PRECISIONS = {"fp32": capi.FP32, "0": capi.FP32, "bf16": capi.BF16, "1": capi.BF16, "f16": capi.F16, "fp16": capi.F16,
+              "3": capi.F16}
 
 
 def _dist_env():
@@ -48,38 +55,70 @@ def find_read_files(wrk_base, recursive=1):
     return sorted(files)
 
 
+def plan_files(files, world, rank):
+    """Which files this rank reads, and whether it takes a shard of each.
+
+    With at least ``world`` files the FILES are dealt out (largest first onto the least loaded rank, so every
+    rank reads only its own input); otherwise every rank reads every file and keeps its contiguous read range
+    balanced by mapped events.  -> (files of this rank, shard_within_file)"""
+    if world == 1:
+        return list(files), False
+    if len(files) < world:
+        return list(files), True
+    load = [0] * world
+    mine = []
+    for size, path in sorted(((os.path.getsize(f), f) for f in files), key=lambda t: (-t[0], t[1])):
+        k = min(range(world), key=lambda i: (load[i], i))
+        load[k] += size
+        if k == rank:
+            mine.append(path)
+    return sorted(mine), False
+
+
 def filter_reads(batch, contig_names, moptions):
-    """Read-level filters of handle_record: --ConUnk (:502) and --region (:505-559)."""
+    """Read-level filters of handle_record: --ConUnk (:502) and --region (:505-559), all reads at once.
+
+    The region test uses ``pos`` and ``len(m_event)`` as they are BEFORE the first/last-match trimming when the
+    batch carries them (``aln_pos`` / ``aln_events``); otherwise the trimmed alignment's first position and event
+    count, which differ only for alignments that start or end with mismatches.  -> indices to keep, or None = all."""
     n = len(batch["start_clip"])
-    keep = np.ones(n, dtype=bool)
     regions = moptions.get("region") or [[None, None, None]]
     con_unk = moptions.get("ConUnk", True)
-    trivial = con_unk and any(r[0] in ("", None) and r[1] in ("", None) and r[2] in ("", None) for r in regions)
-    if trivial:
+    if con_unk and any(r[0] in ("", None) and r[1] in ("", None) and r[2] in ("", None) for r in regions):
         return None
-    lmap = synth.n_windows(batch)
-    col_off = batch["col_off"]
-    for r in range(n):
-        name = contig_names[int(batch["contig"][r])]
-        if (not con_unk) and any(ch in name for ch in "_-/:"):
-            keep[r] = False
-            continue
-        c0, c1 = int(col_off[r]), int(col_off[r + 1])
-        pos = int(batch["col_refpos"][c0:c1].min()) if c1 > c0 else 0
-        ok = False
-        for cr in regions:
-            if cr[0] in ("", None, name) and (cr[1] in ("", None) or pos > cr[1]) and \
-                    (cr[2] in ("", None) or pos + int(lmap[r]) < cr[2]):
-                ok = True
-                break
-        keep[r] = ok
-    return np.flatnonzero(keep)
+    contig = np.asarray(batch["contig"], np.int64)
+    keep = np.ones(n, dtype=bool)
+    if not con_unk:
+        odd = np.array([any(ch in name for ch in "_-/:") for name in contig_names], dtype=bool)
+        keep &= ~odd[contig]
+    if batch.get("aln_pos") is not None:
+        pos = np.asarray(batch["aln_pos"], np.int64)
+    else:
+        col_off = np.asarray(batch["col_off"], np.int64)
+        pos = np.zeros(n, np.int64)
+        has = col_off[1:] > col_off[:-1]
+        if has.any():
+            pos[has] = np.minimum.reduceat(np.asarray(batch["col_refpos"], np.int64), col_off[:-1][has])
+    n_ev = np.asarray(batch["aln_events"], np.int64) if batch.get("aln_events") is not None else synth.n_windows(batch)
+    ok = np.zeros(n, dtype=bool)
+    for cr in regions:
+        m = np.ones(n, dtype=bool)
+        if cr[0] not in ("", None):
+            m &= contig == (contig_names.index(cr[0]) if cr[0] in contig_names else -1)
+        if cr[1] not in ("", None):
+            m &= pos > cr[1]
+        if cr[2] not in ("", None):
+            m &= pos + n_ev < cr[2]
+        ok |= m
+    return np.flatnonzero(keep & ok)
 
 
 def split_for_calls(batch, max_windows=MAX_WINDOWS_PER_CALL):
     """Contiguous read ranges of at most ``max_windows`` mapped events each."""
     w = synth.n_windows(batch)
     n = len(w)
+    if n == 0 or int(w.sum()) <= max_windows:
+        return [(0, n)]
     out, lo, acc = [], 0, 0
     for r in range(n):
         if acc + int(w[r]) > max_windows and r > lo:
@@ -91,33 +130,92 @@ def split_for_calls(batch, max_windows=MAX_WINDOWS_PER_CALL):
     return out
 
 
-def detect_handler(moptions, ctx, read_files, contig_names, failed):
+class Prefetcher(object):
+    """Runs ``load(item)`` for every item on a thread, ``depth`` results ahead of the consumer (numpy releases the GIL
+    while it reads and copies, so file k+1 loads while the GPU call of file k runs).  Exceptions surface in the
+    consumer, in order."""
+
+    def __init__(self, items, load, depth=2):
+        self._q = queue.Queue(maxsize=depth)
+        self._stop = False
+
+        def work():
+            for it in items:
+                if self._stop:
+                    break
+                try:
+                    self._q.put((it, load(it), None))
+                except BaseException as e:          # noqa: B902 - handed to the consumer
+                    self._q.put((it, None, e))
+                    break
+            self._q.put(None)
+        self._t = threading.Thread(target=work, daemon=True)
+        self._t.start()
+
+    def __iter__(self):
+        while True:
+            got = self._q.get()
+            if got is None:
+                return
+            item, value, err = got
+            if err is not None:
+                raise err
+            yield item, value
+
+    def close(self):
+        self._stop = True
+        while self._t.is_alive():
+            try:
+                self._q.get(timeout=0.05)
+            except queue.Empty:
+                pass
+
+
+def load_packed(path, contig_names, moptions, shard=None):
+    """One input file -> list of ``PackedBatch`` ready for ``dm_detect_batch`` (filters and sharding applied),
+    with the index of their first read in the file."""
+    batch, names, _ = reads_io.load_reads(path)
+    if list(names) != list(contig_names):
+        raise capi.DeepModError("%s was packed against a different contig table" % path)
+    first = np.arange(len(batch["start_clip"]), dtype=np.int64)
+    idx = filter_reads(batch, contig_names, moptions)
+    if idx is not None:
+        batch, first = synth.take_reads(batch, idx), first[idx]
+    if shard is not None:
+        rank, world = shard
+        mine = synth.shard_by_windows(batch, world)[rank]
+        batch, first = synth.take_reads(batch, mine), first[mine]
+    out = []
+    for lo, hi in split_for_calls(batch):
+        sub = batch if (lo, hi) == (0, len(batch["start_clip"])) else synth.slice_reads(batch, lo, hi)
+        out.append((capi.PackedBatch(sub), first[lo:hi]))
+    return out
+
+
+def detect_handler(moptions, ctx, read_files, contig_names, failed, shard=None, detail=None):
     """Per-GPU worker: run every packed batch assigned to this rank through the C ABI.
 
-    ``failed`` collects ``{reason: [read ids]}`` like ``sp_options["Error"]`` (:54-57).
-    Returns (reads seen, windows predicted).
-    """
-    world, rank, _ = _dist_env()
+    ``failed`` collects ``{reason: [read ids]}`` like ``sp_options["Error"]`` (:54-57); ``detail`` (a
+    ``predetail.DetailWriter``) receives the per-read predictions when the per-read output is wanted (:716-782).
+    Returns (reads seen, windows predicted)."""
     n_reads = n_windows = 0
-    for path in read_files:
-        batch, names, _ = reads_io.load_reads(path)
-        if list(names) != list(contig_names):
-            raise capi.DeepModError("%s was packed against a different contig table" % path)
-        idx = filter_reads(batch, contig_names, moptions)
-        if idx is not None:
-            batch = synth.take_reads(batch, idx)
-        if world > 1:
-            batch = synth.take_reads(batch, synth.shard_by_windows(batch, world)[rank])
-        for lo, hi in split_for_calls(batch):
-            sub = batch if (lo, hi) == (0, len(batch["start_clip"])) else synth.take_reads(batch, np.arange(lo, hi))
-            pb = capi.PackedBatch(sub)
-            _, _, status = ctx.detect_batch(pb, want_p1=False, want_pred=False)
-            n_reads += pb.n_reads
-            n_windows += int(pb.n_windows_per_read[status == capi.READ_OK].sum())
-            for code in np.unique(status):
-                if code != capi.READ_OK:
-                    failed.setdefault(capi.STATUS_TEXT[int(code)], []).extend(
-                        "%s#%d" % (os.path.basename(path), lo + int(i)) for i in np.flatnonzero(status == code))
+    pre = Prefetcher(read_files, lambda p: load_packed(p, contig_names, moptions, shard))
+    try:
+        for path, parts in pre:
+            for pb, first in parts:
+                if pb.n_reads == 0:
+                    continue
+                _, pred, status = ctx.detect_batch(pb, want_p1=False, want_pred=detail is not None)
+                n_reads += pb.n_reads
+                n_windows += int(pb.n_windows_per_read[status == capi.READ_OK].sum())
+                for code in np.unique(status):
+                    if code != capi.READ_OK:
+                        failed.setdefault(capi.STATUS_TEXT[int(code)], []).extend(
+                            "%s#%d" % (os.path.basename(path), int(first[int(i)])) for i in np.flatnonzero(status == code))
+                if detail is not None:
+                    detail.add_batch(path, first, pb, pred, status, contig_names)
+    finally:
+        pre.close()
     return n_reads, n_windows
 
 
@@ -140,9 +238,8 @@ def events_from_raw(ctx, path):
                          ev_base=z["ev_base"][off[i]:off[i + 1]]) for i, q in enumerate(z["qnames"])}
 
 
-def detect_handler_sam(moptions, ctx, sam_files, contig_names, failed):
+def detect_handler_sam(moptions, ctx, sam_files, contig_names, failed, shard=None):
     """Same worker for SAM-level input: the CIGAR walk of handle_record (:488-705) runs on the GPU too."""
-    world, rank, _ = _dist_env()
     n_reads = n_windows = 0
     for path in sam_files:
         if os.path.isfile(path[:-4] + ".events.npz"):
@@ -155,7 +252,8 @@ def detect_handler_sam(moptions, ctx, sam_files, contig_names, failed):
         for q, why in skipped.items():
             if why not in ("outside region", "unknown chromosome"):
                 failed.setdefault(why, []).append(q)
-        if world > 1:                                   # contiguous ranges balanced by events
+        if shard is not None:                                # contiguous ranges balanced by events
+            rank, world = shard
             ev = np.diff(arrays["ev_off"])
             cum = np.cumsum(ev)
             total = int(cum[-1]) if len(cum) else 0
@@ -200,18 +298,62 @@ def sum_handler(moptions, ctx, contig_names):
     return written
 
 
+class _Ranks(object):
+    """Host-side control plane of a multi-GPU job (gloo: a handful of small python objects); the data plane is
+    ``dm_reduce_comm`` inside the library."""
+
+    def __init__(self, world, rank):
+        self.world, self.rank = world, rank
+        self.dist = None
+        self._own = False
+        if world > 1:
+            import torch.distributed as dist
+            self.dist = dist
+            if not dist.is_initialized():
+                dist.init_process_group("gloo")
+                self._own = True
+
+    def broadcast(self, obj):
+        if self.dist is None:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def gather(self, obj):
+        if self.dist is None:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
+
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            if self._own:
+                self.dist.destroy_process_group()
+
+
 def mDetect_manager(moptions):
     """Drop-in for ``myDetect.mDetect_manager`` on packed read batches."""
     world, rank, local = _dist_env()
     out_level = moptions.get("outLevel", OUTPUT_WARNING)
     while moptions.get("wrkBase") and moptions["wrkBase"][-1] in "/\\":          # :1127-1128
         moptions["wrkBase"] = moptions["wrkBase"][:-1]
-    if moptions.get("predDet", 1) != 1:
-        raise capi.DeepModError("--predDet 0 (summarise stored per-read HDF5 predictions) is outside the GPU hot path")
     if moptions.get("fnum", 7) != 7 or moptions.get("hidden", 100) != 100 or moptions.get("windowsize", 21) != 21:
         raise capi.DeepModError("only the shipped wd21_f7 / 100-hidden-unit architecture is supported")
     if moptions.get("outputlayer", "") not in ("", None):
         raise capi.DeepModError("--outputlayer sigmoid has no shipped model and is not supported")
+    if moptions.get("mod_cluster", 0) not in (0, "0", False, None):
+        # myDetect.py:1061-1072 is marked "revised; should not used now" and reads a global that does not exist
+        raise capi.DeepModError("--mod_cluster 1 is dead code in the reference (myDetect.py:1061) and is not supported; "
+                                "the CpG-cluster second pass is `python -m deepmod_b200.cluster`")
+    if moptions.get("predDet", 1) != 1:
+        from . import predetail
+        return predetail.summarise_stored(moptions)                                # :1232-1263 without the detect phase
+    prec_name = str(moptions.get("precision", "fp32")).lower()
+    if prec_name not in PRECISIONS:
+        raise capi.DeepModError("unknown --precision %s" % prec_name)
     modfile = moptions["modfile"][0] if isinstance(moptions["modfile"], (list, tuple)) else moptions["modfile"]
     model = checkpoint.load_model(modfile)
 
@@ -228,40 +370,60 @@ def mDetect_manager(moptions):
     if rank == 0:
         os.makedirs(out_dir, exist_ok=True)                                         # :1151-1152
 
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        if not dist.is_initialized():
-            torch.cuda.set_device(local)
-            dist.init_process_group("nccl")
-    precision = capi.BF16 if str(moptions.get("precision", "fp32")).lower() in ("bf16", "1") else capi.FP32
+    ranks = _Ranks(world, rank)
+    uid = ranks.broadcast(capi.reduce_unique_id() if (world > 1 and rank == 0) else None)
     ref_seqs = None
     if sam_files:
         contig_names, ref_seqs = reads_io.read_fasta(moptions["Ref"])
         contig_len = np.array([len(x) for x in ref_seqs], np.int64)
     else:
         _, contig_names, contig_len = reads_io.load_reads(read_files[0], header_only=True)
+    my_reads, shard_reads = plan_files(read_files, world, rank)
+    my_sams, shard_sams = plan_files(sam_files, world, rank)
     failed = {}
-    with capi.Context(model, device=local, precision=precision) as ctx:
-        ctx.set_genome(contig_len, moptions["Base"])
-        n_reads, n_windows = detect_handler(moptions, ctx, read_files, contig_names, failed) if read_files else (0, 0)
-        if sam_files:
-            for ci, seq in enumerate(ref_seqs):
-                ctx.set_contig_sequence(ci, seq)
-            nr, nw = detect_handler_sam(moptions, ctx, sam_files, contig_names, failed)
-            n_reads, n_windows = n_reads + nr, n_windows + nw
+    n_reads = n_windows = 0
+    error = None
+    written = []
+    timing = {}
+    with capi.Context(model, device=local, precision=PRECISIONS[prec_name]) as ctx:
+        detail = None
+        try:
+            ctx.set_genome(contig_len, moptions["Base"])
+            if moptions.get("saveDetail", 0):
+                from . import predetail
+                detail = predetail.DetailWriter(out_dir, moptions["wrkBase"], rank, contig_len)
+            if my_reads:
+                n_reads, n_windows = detect_handler(moptions, ctx, my_reads, contig_names, failed,
+                                                    (rank, world) if shard_reads else None, detail)
+            if my_sams:
+                for ci, seq in enumerate(ref_seqs):
+                    ctx.set_contig_sequence(ci, seq)
+                nr, nw = detect_handler_sam(moptions, ctx, my_sams, contig_names, failed,
+                                            (rank, world) if shard_sams else None)
+                n_reads, n_windows = n_reads + nr, n_windows + nw
+            if detail is not None:
+                detail.close()
+        except Exception as e:                      # every rank must reach the exchange below, or the others hang in it
+            error = "%s: %s" % (type(e).__name__, e)
+        timing["predict_s"] = time.time() - start_time
+        # one small object per rank: failure, rejected reads, counts (rank 0 used to report only its own)
+        reports = ranks.gather((error, failed, n_reads, n_windows))
+        errors = ["rank %d: %s" % (i, r[0]) for i, r in enumerate(reports) if r[0]]
+        if errors:
+            ranks.close()
+            raise capi.DeepModError("detect failed on %d of %d ranks: %s" % (len(errors), world, "; ".join(errors)))
+        failed = {}
+        for r in reports:
+            for k, v in r[1].items():
+                failed.setdefault(k, []).extend(v)
+        n_reads, n_windows = sum(r[2] for r in reports), sum(r[3] for r in reports)
         if world > 1:
-            import torch
-            cells = ctx.hist_tensor()
-            dist.all_reduce(cells, op=dist.ReduceOp.SUM)       # the one exchange step of the job
-            counts = torch.tensor([n_reads, n_windows], device=cells.device, dtype=torch.int64)
-            dist.all_reduce(counts)
-            torch.cuda.synchronize()
-            n_reads, n_windows = int(counts[0]), int(counts[1])
+            timing["reduce_ms"] = ctx.reduce_comm(uid, rank, world)      # the one exchange step of the job
         pred_time = time.time() - start_time
-        written = []
         if rank == 0:
+            if detail is not None:
+                from . import predetail
+                predetail.merge_index_files(out_dir, moptions["wrkBase"])            # :1193-1221
             if failed:
                 print("Error information for different fast5 files:")                # :1223-1226
                 for k, v in failed.items():
@@ -270,13 +432,13 @@ def mDetect_manager(moptions):
             moptions["outFolder"] = out_dir                                         # :1228
             t1 = time.time()
             written = sum_handler(moptions, ctx, contig_names)
+            timing["summary_s"] = time.time() - t1
             print("Genomic-position Detection consuming time %d" % (time.time() - t1))
             if out_level <= OUTPUT_INFO:
-                print("reads=%d bases=%d (%.3g bases/s) beds=%d" % (n_reads, n_windows, n_windows / max(pred_time, 1e-9),
-                                                                    len(written)))
+                print("reads=%d bases=%d (%.4g bases/s in the prediction phase) beds=%d %s" % (
+                    n_reads, n_windows, n_windows / max(timing["predict_s"], 1e-9), len(written), timing))
             with open(out_dir + ".done", "a"):                                      # :1263
                 os.utime(out_dir + ".done", None)
-    if world > 1:
-        dist.barrier()
+    ranks.close()
     sys.stdout.flush()
-    return {"reads": n_reads, "bases": n_windows, "beds": written, "failed": failed}
+    return {"reads": n_reads, "bases": n_windows, "beds": written, "failed": failed, "timing": timing}

@@ -7,7 +7,12 @@ memory from FAST5 + SAM before calling ``get_Feature`` (``myDetect.py:392-456``,
 import numpy as np
 
 BATCH_KEYS = ("ev_off", "ev_mean", "ev_stdv", "ev_len", "ev_base", "col_off", "col_refbase", "col_readbase",
-              "col_refpos", "start_clip", "end_clip", "contig", "strand")
+              "col_refpos", "start_clip", "end_clip", "contig", "strand", "aln_pos", "aln_events", "read_id")
+# Optional per-read arrays: ``ev_base`` (k-mer centres for the :868 check); ``aln_pos`` / ``aln_events`` = the 0-based
+# alignment start after the removal of leading non-aligned CIGAR ops and the number of events left after clipping, i.e.
+# ``pos`` and ``len(m_event)`` as the --region test sees them BEFORE the first/last-match trimming
+# (myDetect.py:517-559); without them the filter uses the trimmed alignment (identical unless the alignment starts
+# or ends with mismatches); ``read_id`` = fixed-width byte strings naming the reads in the per-read detail output.
 
 
 def save_reads(path, batch, contig_names, contig_len):

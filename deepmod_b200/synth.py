@@ -156,20 +156,44 @@ def n_windows(batch):
     return (L - batch["start_clip"] - batch["end_clip"]).astype(np.int64)
 
 
+PER_READ_KEYS = ("start_clip", "end_clip", "contig", "strand", "aln_pos", "aln_events", "read_id")   # the last three are optional
+EVENT_KEYS = ("ev_mean", "ev_stdv", "ev_len", "ev_base")                                    # ev_base is optional
+COLUMN_KEYS = ("col_refbase", "col_readbase", "col_refpos")
+
+
+def slice_reads(batch, lo, hi):
+    """Reads [lo, hi) of a packed batch as VIEWS (no copy of the event / column arrays)."""
+    e0, e1 = int(batch["ev_off"][lo]), int(batch["ev_off"][hi])
+    c0, c1 = int(batch["col_off"][lo]), int(batch["col_off"][hi])
+    out = {k: batch[k][e0:e1] for k in EVENT_KEYS if batch.get(k) is not None}
+    out.update({k: batch[k][c0:c1] for k in COLUMN_KEYS})
+    out["ev_off"] = (batch["ev_off"][lo:hi + 1] - e0).astype(np.int64)
+    out["col_off"] = (batch["col_off"][lo:hi + 1] - c0).astype(np.int64)
+    out.update({k: batch[k][lo:hi] for k in PER_READ_KEYS if batch.get(k) is not None})
+    return out
+
+
+def _gather_segments(arr, off, idx):
+    """Concatenation of arr[off[r]:off[r+1]] for r in idx, without a python loop per read."""
+    lens = (off[idx + 1] - off[idx]).astype(np.int64)
+    total = int(lens.sum())
+    if total == 0:
+        return arr[:0]
+    starts = np.repeat(off[idx] - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens)
+    return arr[starts + np.arange(total, dtype=np.int64)]
+
+
 def take_reads(batch, idx):
-    """Sub-batch of the given read indices (keeps the packed layout)."""
+    """Sub-batch of the given read indices (keeps the packed layout; optional arrays stay optional)."""
     idx = np.asarray(idx, dtype=np.int64)
-    ev_sl = [slice(int(batch["ev_off"][r]), int(batch["ev_off"][r + 1])) for r in idx]
-    co_sl = [slice(int(batch["col_off"][r]), int(batch["col_off"][r + 1])) for r in idx]
-    out = {}
-    for k in ("ev_mean", "ev_stdv", "ev_len", "ev_base"):
-        out[k] = np.concatenate([batch[k][s] for s in ev_sl]) if len(idx) else batch[k][:0]
-    for k in ("col_refbase", "col_readbase", "col_refpos"):
-        out[k] = np.concatenate([batch[k][s] for s in co_sl]) if len(idx) else batch[k][:0]
-    out["ev_off"] = np.concatenate([[0], np.cumsum([s.stop - s.start for s in ev_sl])]).astype(np.int64)
-    out["col_off"] = np.concatenate([[0], np.cumsum([s.stop - s.start for s in co_sl])]).astype(np.int64)
-    for k in ("start_clip", "end_clip", "contig", "strand"):
-        out[k] = batch[k][idx]
+    if len(idx) and np.array_equal(idx, np.arange(idx[0], idx[0] + len(idx))):
+        return slice_reads(batch, int(idx[0]), int(idx[0]) + len(idx))
+    ev_off, col_off = np.asarray(batch["ev_off"], np.int64), np.asarray(batch["col_off"], np.int64)
+    out = {k: _gather_segments(batch[k], ev_off, idx) for k in EVENT_KEYS if batch.get(k) is not None}
+    out.update({k: _gather_segments(batch[k], col_off, idx) for k in COLUMN_KEYS})
+    out["ev_off"] = np.concatenate([[0], np.cumsum(ev_off[idx + 1] - ev_off[idx])]).astype(np.int64)
+    out["col_off"] = np.concatenate([[0], np.cumsum(col_off[idx + 1] - col_off[idx])]).astype(np.int64)
+    out.update({k: batch[k][idx] for k in PER_READ_KEYS if batch.get(k) is not None})
     return out
 
 

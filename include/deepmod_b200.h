@@ -44,14 +44,18 @@ enum dm_status {
   DM_ERR_ARG = -1,
   DM_ERR_CUDA = -2,
   DM_ERR_STATE = -3,
-  DM_ERR_IO = -4
+  DM_ERR_IO = -4,
+  DM_ERR_OVERFLOW = -5,  /* a per-position counter reached its limit (2^28 - 1): the accumulator is no longer exact */
+  DM_ERR_NCCL = -6
 };
 
 /* arithmetic of the BiLSTM */
 enum dm_precision {
   DM_FP32 = 0,   /* fp32 FMA + accurate expf/tanhf: the parity path (<=1e-4 on p1) */
   DM_BF16 = 1,   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM; CTA pairs (cta_group::2) */
-  DM_BF16_1CTA = 2  /* same arithmetic, one CTA per 128-window tile (cta_group::1); kept for A/B measurements */
+  DM_BF16_1CTA = 2, /* same arithmetic, one CTA per 128-window tile (cta_group::1); kept for A/B measurements */
+  DM_F16 = 3     /* fp16 operands (weights and hidden state) on the same tensor-core kernel: same rate as DM_BF16,
+                    three more mantissa bits on every operand; the throughput default */
 };
 
 /* per-read status written by dm_detect_batch (mirrors sp_param['f5status']) */
@@ -113,10 +117,33 @@ int dm_forward_windows(dm_ctx* ctx, int64_t n, const float* X, float* p1_out, ui
  * for `base` (the --Base of interest, bin/DeepMod.py:331). */
 int dm_set_genome(dm_ctx* ctx, int32_t n_contigs, const int64_t* contig_len, char base);
 int dm_hist_clear(dm_ctx* ctx);
-/* Device pointer + length (in uint64 cells) of the whole accumulator, for the one
- * end-of-job NCCL sum across GPUs (each cell packs three 21-bit counters, so a
- * sum of cells is the sum of counters). */
+/* Device pointer + length (in uint64 cells) of the whole accumulator (cell = cov | mod << 28 | key-created
+ * flag << 56, so a sum of cells is the sum of counters; dm_reduce* is the supported way to merge GPUs). */
 int dm_hist_device_ptr(dm_ctx* ctx, void** cells_d, int64_t* n_cells);
+
+/* ---- the job's single exchange step: sum of the accumulators of all GPUs ----------------
+ * Reference equivalent: the dict accumulation over all reads (myDetect.py:1089-1100) and the offline merge of
+ * per-run BED files, DeepMod_tools/sum_chr_mod.py:36-63.  Integer sums: bit-exact in any order.  Afterwards
+ * EVERY context holds the merged accumulator.  NCCL (libnccl.so.2) is loaded on first use; without it these
+ * calls fail with DM_ERR_NCCL.  Both check max(cov) * ranks against the counter limit first and return
+ * DM_ERR_OVERFLOW on every rank, without summing, if the merged counters might not fit.
+ *
+ * One process driving n contexts on n distinct devices (ncclCommInitAll + one grouped ncclAllReduce): */
+int dm_reduce(dm_ctx** ctxs, int n);
+/* One process per GPU: rank 0 makes an id (dm_reduce_unique_id), the host shares its 128 bytes with the other
+ * ranks by any means, then every rank calls dm_reduce_comm(ctx, id, rank, n).  The communicator is kept in the
+ * context: later calls may pass id == NULL. */
+int dm_reduce_unique_id(uint8_t id_out[128]);
+int dm_reduce_comm(dm_ctx* ctx, const uint8_t* id, int rank, int n_ranks);
+/* dst += src for two contexts of ONE process holding the same genome (same or different GPU of the box): counters
+ * add, key-created flags OR -- the merge of DeepMod_tools/sum_chr_mod.py:47-52 without going through BED files. */
+int dm_hist_merge(dm_ctx* dst, dm_ctx* src);
+/* Conservation counters of the accumulator (what a merge must preserve): sum of cov, sum of mod, number of
+ * existing rows (cells != 0), and a position-weighted checksum (sum over cells of (cov + 3 mod) * (index mod 65521 + 1),
+ * mod 2^64) that is linear in the cells like the counters themselves.  Any output may be NULL. */
+int dm_hist_totals(dm_ctx* ctx, uint64_t* sum_cov, uint64_t* sum_mod, uint64_t* n_rows, uint64_t* checksum);
+/* Device time of the last exchange (CUDA events around the all-reduce on the context's stream). */
+int dm_last_reduce_ms(const dm_ctx* ctx, float* ms);
 /* Rows that exist in the reference's dict for (contig, strand): positions touched
  * by at least one alignment column whose refbase == base (deletions included,
  * myDetect.py:1093-1094), ascending.  Call with pos == NULL to get the count. */
@@ -126,6 +153,12 @@ int dm_hist_nonzero(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t cap,
  * (myDetect.py:1116-1120).  No file is created when there are no rows (:1109). */
 int dm_write_bed(dm_ctx* ctx, int32_t contig, int8_t strand, const char* chrom,
                  const char* path, int64_t* n_rows);
+
+/* sum_handler's loop over STORED per-read predictions (--predDet 0: read_pred_detail + myDetect.py:1089-1100): n
+ * records of one read mapped to (contig, strand) -- the columns of its `predetail` dataset (:720-753): reference base,
+ * read base ('-' = deletion), reference position, stored prediction -- accumulate exactly like dm_detect_batch's. */
+int dm_accumulate_records(dm_ctx* ctx, int32_t contig, int8_t strand, int64_t n, const uint8_t* refbase,
+                          const uint8_t* readbase, const int64_t* refpos, const int8_t* mod_pred);
 
 /* Overwrite cells of (contig, strand) with summary rows read elsewhere (e.g. BED files of earlier runs:
  * DeepMod_tools/sum_chr_mod.py:36-45 readbed2); deletion-touch counters of those cells become 0. */

@@ -1,10 +1,10 @@
 """Oracle-side model of the GPU accumulator: one uint64 cell per (contig, strand, position) packing
-three 21-bit counters (cov, mod, deletion touches).  Test infrastructure only: it lets the CPU
+cov (28 bits), mod (28 bits) and a key-created flag field (8 bits: 0/1 per rank, deletions).  Test infrastructure only: it lets the CPU
 tests check that a SUM of per-shard cell arrays equals the reference's merged dict
 (myDetect.py:1089-1100 accumulated over all reads; DeepMod_tools/sum_chr_mod.py:47-52)."""
 import numpy as np
 
-COV_SHIFT, MOD_SHIFT, DEL_SHIFT, MASK = 0, 21, 42, (1 << 21) - 1
+COV_SHIFT, MOD_SHIFT, DEL_SHIFT, MASK = 0, 28, 56, (1 << 28) - 1
 
 
 def cells_from_reads(batch, contig_len, base, preds_by_read, status):
@@ -26,7 +26,7 @@ def cells_from_reads(batch, contig_len, base, preds_by_read, status):
             gap = readb[i] == ord("-")
             if refb[i] == bcode:
                 if gap:
-                    cells[sbase + pos[i]] += 1 << DEL_SHIFT
+                    cells[sbase + pos[i]] |= 1 << DEL_SHIFT
                 else:
                     cells[sbase + pos[i]] += (1 << COV_SHIFT) + ((1 << MOD_SHIFT) if pred[k] == 1 else 0)
             if not gap:

@@ -136,7 +136,7 @@ def test_accumulate_is_additive_and_clearable(capi, golden_batch):
         assert all(np.array_equal(x, y) for x, y in zip(a, d))
 
 
-@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("precision", [0, 1, 3])
 def test_pipelined_detect_equals_single_pass(capi, golden_batch, precision):
     """dm_detect_batch cut into sub-batches over two streams (dm_set_pipeline): same probabilities, labels,
     statuses and per-position counts as one pass; reads are independent and the reducer is a sum."""
@@ -180,28 +180,50 @@ def test_umma_selftest(capi):
             assert err < 2e-3 * np.sqrt(k), (n, k, err)
 
 
-def test_forward_windows_bf16(capi, model_tag):
-    """bf16 tensor-core path: not a 1e-4 path; bounded error + reported flip rate."""
+# Tensor-core path: not a 1e-4 path.  Its error is GATED at <= 2x what was measured on B200 (round 2:
+# golden windows, three models: fp16 operands mean |dp1| 2.8e-4 / max 5.4e-3; bf16 operands 6.0e-4 / 1.0e-2; at most
+# 2 of 2048 argmax flips), so that a kernel regression cannot hide behind a loose bound.
+TC_BOUNDS = {3: dict(mean=6e-4, max=1.5e-2, flips=4), 1: dict(mean=1.2e-3, max=3e-2, flips=4)}
+
+
+@pytest.mark.parametrize("precision", [3, 1])
+def test_forward_windows_tensor_core(capi, model_tag, precision):
     g = golden_windows(model_tag)
-    with make_ctx(capi, model_tag, 1) as ctx:
+    with make_ctx(capi, model_tag, precision) as ctx:
         p1, pred = ctx.forward_windows(g["X"])
     err = np.abs(p1.astype(np.float64) - g["p1"])
-    flips = float(np.mean(pred != g["pred"]))
-    print("bf16 %s: max |dp1| %.3g mean %.3g flip rate %.4f" % (model_tag, err.max(), err.mean(), flips))
-    assert err.mean() < 0.01 and flips < 0.02 and np.quantile(err, 0.99) < 0.1
+    flips = int(np.sum(pred != g["pred"]))
+    print("%s %s: max |dp1| %.3g mean %.3g flips %d / %d" % ({3: "f16", 1: "bf16"}[precision], model_tag, err.max(), err.mean(),
+                                                           flips, len(pred)))
+    b = TC_BOUNDS[precision]
+    assert err.mean() <= b["mean"] and err.max() <= b["max"] and flips <= b["flips"]
+    # a flipped label must be a window the oracle itself puts at the decision boundary
+    assert np.all(np.abs(g["p1"][pred != g["pred"]] - 0.5) < 0.02)
 
 
-def test_detect_batch_bf16_close(capi, golden_batch, tmp_path):
+@pytest.mark.parametrize("precision", [3, 1])
+def test_detect_batch_tensor_core_bed_level(capi, golden_batch, tmp_path, precision):
+    """What the tensor-core arithmetic does to the DELIVERABLE: rows of the golden BED whose mod count / percentage
+    differ from the fp32 / oracle BED.  Coverage and the set of rows never depend on the model: bit-exact."""
     batch, names, lens = golden_batch
-    p1, pred, beds, hist, g = _check_reads(capi, "conmodC_P100", batch, names, lens, 1, tmp_path)
-    flips = float(np.mean(pred != g["pred"]))
-    print("bf16 reads: flip rate %.4f, mean |dp1| %.3g" % (flips, np.abs(p1 - g["p1"]).mean()))
-    assert flips < 0.02
-    # coverage does not depend on the model: bit-exact even on the bf16 path
+    p1, pred, beds, hist, g = _check_reads(capi, "conmodC_P100", batch, names, lens, precision, tmp_path)
+    flips = int(np.sum(pred != g["pred"]))
+    err = np.abs(p1 - g["p1"])
+    n_rows = n_mod_diff = n_pct_diff = 0
+    assert sorted(beds) == sorted(g["bed"])
     for key, text in g["bed"].items():
-        rows = [ln.split(" ") for ln in text.splitlines()]
-        pos, cov, mod = hist[(names.index(key[:-1]), key[-1])]
-        assert [int(r[1]) for r in rows] == list(pos) and [int(r[9]) for r in rows] == list(cov)
+        want = [ln.split(" ") for ln in text.splitlines()]
+        got = [ln.split(" ") for ln in beds[key].splitlines()]
+        assert [r[:10] for r in got] == [r[:10] for r in want]          # chr, pos, base, capped cov, strand, ..., cov
+        n_rows += len(want)
+        n_mod_diff += sum(a[11] != b[11] for a, b in zip(got, want))
+        n_pct_diff += sum(a[10] != b[10] for a, b in zip(got, want))
+    print("%s reads: %d windows, %d label flips, mean |dp1| %.3g max %.3g; BED rows %d, mod differs on %d, percentage on %d" % (
+        {3: "f16", 1: "bf16"}[precision], len(pred), flips, err.mean(), err.max(), n_rows, n_mod_diff, n_pct_diff))
+    b = TC_BOUNDS[precision]
+    assert flips <= max(4, int(1e-3 * len(pred))) and err.mean() <= b["mean"] and err.max() <= 10 * b["max"]
+    assert n_mod_diff <= flips and n_pct_diff <= flips                 # a row can only change through a flipped label
+    assert n_mod_diff <= max(2, int(1e-3 * n_rows))
 
 
 def test_session_seam_drives_the_reference_batch_loop(capi, golden_batch):

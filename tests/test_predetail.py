@@ -1,0 +1,143 @@
+"""Per-read detail output + index files + --predDet 0: host logic on CPU, the round trip on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from deepmod_b200 import capi, predetail, reads_io, synth
+from oracle import detect_ref, ref_harness
+
+
+@pytest.fixture(scope="module")
+def packed():
+    genome = synth.make_genome([30000, 12000], seed=11)
+    batch = synth.make_reads(genome, 24, seed=12, align_seed=13, mean_len=500, len_lo=70, len_hi=2500)
+    pb = capi.PackedBatch(batch)
+    rng = np.random.default_rng(5)
+    pred = (rng.random(pb.n_windows) < 0.3).astype(np.uint8)
+    status = np.where(pb.n_windows_per_read > 0, capi.READ_OK, capi.READ_LESS_EVENT).astype(np.int32)
+    status[3] = capi.READ_MISMATCH                      # a read rejected by the k-mer check: no detail, no counts
+    return batch, pb, pred, status
+
+
+def test_column_predictions_equal_reference_write_back(packed):
+    batch, pb, pred, status = packed
+    got = predetail.column_predictions(pb, pred, status)
+    win_off = np.concatenate([[0], np.cumsum(pb.n_windows_per_read)])
+    for r in range(pb.n_reads):
+        rd = detect_ref.unpack_read(batch, r)
+        c0, c1 = int(batch["col_off"][r]), int(batch["col_off"][r + 1])
+        if status[r] != capi.READ_OK:
+            assert not got[c0:c1].any()
+            continue
+        want = detect_ref.write_back(pred[win_off[r]:win_off[r + 1]], rd["readbase"])       # myDetect.py:824-833
+        assert np.array_equal(got[c0:c1], want)
+
+
+def test_detail_container_and_index_files(packed, tmp_path):
+    batch, pb, pred, status = packed
+    names = ["chrA", "chr_B"]
+    out_dir = str(tmp_path / "out" / "mod")
+    wrk = str(tmp_path / "in")
+    os.makedirs(wrk)
+    w = predetail.DetailWriter(out_dir, wrk, rank=0, contig_len=[30000, 12000])
+    first = np.arange(pb.n_reads)
+    w.add_batch(os.path.join(wrk, "sub", "b0.dmreads.npz"), first, pb, pred, status, names)
+    ok = np.flatnonzero(status == capi.READ_OK)
+    # per-batch index files: one per chromosome, sorted by (chr, strand, pos), reference line format (:776-779)
+    lines = []
+    for ci, nm in enumerate(names):
+        p = os.path.join(out_dir, "0", "%s.rnn.pred.ind.0" % nm)
+        assert os.path.isfile(p)
+        txt = open(p).read()
+        assert txt.endswith(" \n")
+        rows = [l.split(" ") for l in txt.splitlines()]
+        assert all(r[0] == nm and r[-1] == "" and len(r) == 7 for r in rows)
+        assert rows == sorted(rows, key=lambda r: (r[0], r[1], int(r[2]), r[3], r[4], r[5]))
+        lines += rows
+    assert len(lines) == len(ok)
+    assert {r[3] for r in lines} == {"pred_%d" % r for r in ok}
+    assert all(r[4].startswith("sub/b0.dmreads.npz#") and r[5] == "0/rnn.pred.detail.dmpd.0" for r in lines)
+    # records reduce to the same dict as the direct path (myDetect.py:1089-1100)
+    recs = predetail.records_of(os.path.join(out_dir, "0", "rnn.pred.detail.dmpd.0"))
+    acc_detail, acc_direct = {}, {}
+    mod = predetail.column_predictions(pb, pred, status)
+    for r in ok:
+        attrs, rec = recs["pred_%d" % r]
+        rd = detect_ref.unpack_read(batch, r)
+        assert rec.dtype == predetail.DETAIL_DTYPE and rec.dtype.itemsize == 26
+        assert attrs["mapped_chr"] == names[rd["contig"]] and attrs["mapped_strand"] == rd["strand"]
+        assert [x.decode() for x in rec["refbase"]] == list(rd["refbase"])
+        assert [x.decode() for x in rec["readbase"]] == list(rd["readbase"])
+        assert np.array_equal(rec["refbasei"], np.asarray(rd["refpos"], np.uint64))
+        lo, hi = (rec["refbasei"][0], rec["refbasei"][-1]) if rd["strand"] == "+" else (rec["refbasei"][-1], rec["refbasei"][0])
+        assert (attrs["mapped_start"], attrs["mapped_end"]) == (lo, hi)                       # :731-732
+        assert attrs["clipped_bases_start"] == rd["start_clip"] and attrs["clipped_bases_end"] == rd["end_clip"]
+        assert attrs["pred_mod_num"] == int(rec["mod_pred"].sum())
+        assert attrs["num_matches"] + attrs["num_mismatches"] + attrs["num_insertions"] + attrs["num_deletions"] == len(rec)
+        c0 = int(batch["col_off"][r])
+        detect_ref.reduce_read(acc_detail, attrs["mapped_chr"], attrs["mapped_strand"], "C", [x.decode() for x in rec["refbase"]],
+                               [x.decode() for x in rec["readbase"]], rec["refbasei"], rec["mod_pred"])
+        detect_ref.reduce_read(acc_direct, names[rd["contig"]], rd["strand"], "C", rd["refbase"], rd["readbase"], rd["refpos"],
+                               mod[c0:c0 + len(rec)])
+    assert acc_detail == acc_direct and len(acc_direct) > 100
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted")
+def test_merged_index_is_read_by_the_unmodified_read_file_list(packed, tmp_path):
+    """The merged rnn.pred.ind.<chr> (myDetect.py:1193-1221) goes through the reference's own reader (:989-1010)."""
+    batch, pb, pred, status = packed
+    names = ["chrA", "chrB"]
+    out_dir = str(tmp_path / "o" / "mod")
+    wrk = str(tmp_path / "in")
+    os.makedirs(wrk)
+    half = pb.n_reads // 2
+    for rank, (lo, hi) in enumerate(((0, half), (half, pb.n_reads))):                 # two ranks' ctfolders
+        sub = capi.PackedBatch(synth.slice_reads(batch, lo, hi))
+        w0 = int(pb.n_windows_per_read[:lo].sum())
+        w = predetail.DetailWriter(out_dir, wrk, rank=rank, contig_len=[30000, 12000])
+        w.add_batch(os.path.join(wrk, "b.dmreads.npz"), np.arange(lo, hi), sub, pred[w0:w0 + sub.n_windows], status[lo:hi], names)
+    merged = predetail.merge_index_files(out_dir, wrk)
+    assert [os.path.basename(m) for m in merged] == ["rnn.pred.ind.chrA", "rnn.pred.ind.chrB"]
+    md = ref_harness.import_myDetect()
+    total = 0
+    for path, chrom in zip(merged, names):
+        head = open(path).read().splitlines()[:2]
+        assert head == ["#base_folder_fast5 %s " % wrk, "#base_folder_output %s " % os.path.abspath(out_dir)]
+        for strand in "+-":
+            sp = {}
+            md.read_file_list(path, chrom, strand, sp)                                  # the reference's reader
+            mine, base_out = predetail.read_file_list(path, strand)
+            assert sp["handlingList"] == mine
+            assert sp["base_folder_output"] == base_out == os.path.abspath(out_dir)     # absolute: no '/' appended (:1000)
+            assert sp["base_folder_fast5"] == wrk
+            pos = [int(l[2]) for l in mine]
+            assert pos == sorted(pos)
+            for l in mine:                                                               # what read_pred_detail opens (:1016)
+                assert os.path.isfile(base_out + "/" + l[5])
+            total += len(mine)
+    assert total == int((status == capi.READ_OK).sum())
+
+
+@pytest.mark.gpu
+def test_saved_detail_resumes_to_the_same_bed(tmp_path):
+    """detect --saveDetail 1, then detect --predDet 0 --predpath: identical BED files (myDetect.py:1232-1263)."""
+    from deepmod_b200 import cli
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    genome = synth.make_genome([40000, 15000], seed=21)
+    wrk = tmp_path / "reads"
+    wrk.mkdir()
+    for i in range(3):
+        b = synth.make_reads(genome, 12, seed=30 + i, align_seed=40 + i, mean_len=700, len_lo=70, len_hi=3000)
+        reads_io.save_reads(str(wrk / ("part%d.dmreads.npz" % i)), b, ["c1", "c2"], [40000, 15000])
+    out1, out2 = str(tmp_path / "o1"), str(tmp_path / "o2")
+    res = cli.main(["detect", "--wrkBase", str(wrk), "--modfile", os.path.join(gold, "model_conmodC_P100.npz"), "--outFolder", out1,
+                    "--FileID", "run", "--Base", "C", "--saveDetail", "1"])
+    assert res["beds"]
+    assert sorted(os.listdir(os.path.join(out1, "run", "0")))[0].endswith(".rnn.pred.ind.0")
+    res2 = cli.main(["detect", "--wrkBase", str(wrk), "--predDet", "0", "--predpath", os.path.join(out1, "run"), "--outFolder", out2,
+                     "--FileID", "resumed", "--Base", "C"])
+    assert len(res2["beds"]) == len(res["beds"])
+    for p in res["beds"]:
+        q = os.path.join(out2, "resumed", os.path.basename(p))
+        assert open(p).read() == open(q).read(), os.path.basename(p)

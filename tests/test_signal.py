@@ -68,3 +68,35 @@ def test_gpu_event_stats_bit_exact():
     print("event stats: %d events, %d samples, %d mismatching values, %.3f ms" % (len(m), len(raw), bad, ms))
     assert np.abs(m - want_m).max() <= 1.001e-3 and np.abs(s - want_s).max() <= 1.001e-3
     assert bad == 0
+
+
+@pytest.mark.gpu
+def test_gpu_event_stats_truncated_raw():
+    """A raw array shorter than its event table says (truncated file): numpy slicing clips the normalisation span
+    and the last events (myDetect.py:266-270, :334-343); the GPU must do the same instead of reading out of bounds."""
+    from deepmod_b200 import capi, checkpoint
+    raw_off, raw, ev_off, start, length = synth.make_raw_signals(6, seed=9, mean_events=300)
+    # cut the tail of reads 1 and 4: their last events now reach past the end of the raw array
+    keep, new_off = [], [0]
+    for r in range(6):
+        x = raw[raw_off[r]:raw_off[r + 1]]
+        if r in (1, 4):
+            last = ev_off[r + 1] - 1
+            x = x[:int(start[last - 3] + length[last - 3] // 2)]
+        keep.append(x)
+        new_off.append(new_off[-1] + len(x))
+    raw2, raw_off2 = np.concatenate(keep), np.array(new_off, np.int64)
+    want_m, want_s = [], []
+    for r in range(6):
+        x = raw2[raw_off2[r]:raw_off2[r + 1]]
+        st, ln = start[ev_off[r]:ev_off[r + 1]], length[ev_off[r]:ev_off[r + 1]]
+        with np.errstate(all="ignore"):
+            sig = signal_ref.normalize(x, st, ln)
+            m, s = signal_ref.event_stats(sig, st, ln)
+        want_m.append(m); want_s.append(s)
+    want_m, want_s = np.concatenate(want_m), np.concatenate(want_s)
+    with capi.Context(checkpoint.random_model(0), 0) as ctx:
+        m, s = ctx.event_stats(raw_off2, raw2, ev_off, start, length)
+    ok = ~np.isnan(want_m)              # events entirely past the end: mean of an empty slice (nan in numpy)
+    assert ok.sum() > len(ok) - 12
+    assert np.array_equal(m[ok], want_m[ok]) and np.array_equal(s[ok], want_s[ok])

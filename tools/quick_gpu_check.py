@@ -20,7 +20,7 @@ for n, k in ((16, 16), (80, 112), (80, 208), (256, 64)):
         print("selftest n=%d k=%d max_err=%.4g" % (n, k, ctx.selftest_umma(n, k)), flush=True)
     except Exception as e:
         print("selftest failed", n, k, e, flush=True)
-for prec, name in ((capi.FP32, "fp32"), (capi.BF16_1CTA, "bf16-1cta"), (capi.BF16, "bf16-pair")):
+for prec, name in ((capi.FP32, "fp32"), (capi.BF16_1CTA, "bf16-1cta"), (capi.BF16, "bf16-pair"), (capi.F16, "f16-pair")):
     ctx.set_precision(prec)
     try:
         p1, pred = ctx.forward_windows(X)
@@ -29,7 +29,7 @@ for prec, name in ((capi.FP32, "fp32"), (capi.BF16_1CTA, "bf16-1cta"), (capi.BF1
     except Exception as e:
         print(name, "failed:", e, flush=True)
 big = np.tile(X, (int(os.environ.get("QC_TILE", "128")), 1, 1))
-for prec, name in ((capi.BF16_1CTA, "bf16-1cta"), (capi.BF16, "bf16-pair")):
+for prec, name in ((capi.BF16_1CTA, "bf16-1cta"), (capi.BF16, "bf16-pair"), (capi.F16, "f16-pair")):
     ctx.set_precision(prec)
     try:
         for it in range(3):
@@ -43,7 +43,7 @@ for prec, name in ((capi.BF16_1CTA, "bf16-1cta"), (capi.BF16, "bf16-pair")):
 
 # attribution runs (development switches of dm_debug_tc_windows): not results, only kernel timings
 small = np.tile(X, (128, 1, 1))
-for prec, name in ((capi.BF16_1CTA, "1cta"), (capi.BF16, "pair")):
+for prec, name in ((capi.BF16_1CTA, "1cta"), (capi.F16, "f16-pair")):
     ctx.set_precision(prec)
     for mode, mname in ((0, "normal"), (0x100, "no-math"), (0x200, "no-mma"), (0x600, "no-mma,no-load"), (0x300, "no-math,no-mma"), (0x700, "only sync"), (0x400, "no-load")):
         try:

@@ -22,17 +22,23 @@ with np.load(os.path.join(gold, "model_conmodC_P100.npz")) as z:
     model = checkpoint.Model.from_dict({k: z[k] for k in z.files})
 with np.load(os.path.join(gold, "windows_conmodC_P100.npz")) as z:
     X, p1g, predg = z["X"], z["p1"], z["pred"]
-ctx = capi.Context(model, 0, capi.BF16)
-p1, pred = ctx.forward_windows(X)
-err = np.abs(p1 - p1g)
 big = np.tile(X, (int(os.environ.get("QC_TILE", "512")), 1, 1))
-ts = []
-for it in range(6):
-    ctx.forward_windows(big)
-    ts.append(ctx.last_timing()[0])
-ts = sorted(ts[1:])
-print("%%-28s max|dp1|=%%.4f flips=%%d  %%d windows: lstm min %%.3f med %%.3f ms -> %%.1f Mbases/s" %% (
-    os.environ.get("VARIANT"), err.max(), int((pred != predg).sum()), len(big), ts[0], ts[len(ts) // 2], len(big) / ts[len(ts) // 2] / 1e3), flush=True)
+for prec in [int(x) for x in os.environ.get("SWEEP_PREC", "1,3").split(",")]:
+    try:
+        ctx = capi.Context(model, 0, prec)
+    except Exception as e:
+        print("%%-28s prec %%d: %%s" %% (os.environ.get("VARIANT"), prec, e), flush=True)
+        continue
+    p1, pred = ctx.forward_windows(X)
+    err = np.abs(p1 - p1g)
+    ts = []
+    for it in range(6):
+        ctx.forward_windows(big)
+        ts.append(ctx.last_timing()[0])
+    ts = sorted(ts[1:])
+    print("%%-28s prec %%d max|dp1|=%%.4f mean=%%.2e flips=%%d/%%d  %%d windows: lstm min %%.3f med %%.3f ms -> %%.1f Mbases/s" %% (
+        os.environ.get("VARIANT"), prec, err.max(), err.mean(), int((pred != predg).sum()), len(pred), len(big), ts[0], ts[len(ts) // 2], len(big) / ts[len(ts) // 2] / 1e3), flush=True)
+    ctx.close()
 ''' % (ROOT, ROOT)
 
 
@@ -51,7 +57,7 @@ def main():
             for f in names:
                 env = dict(os.environ, DEEPMOD_B200_LIB=os.path.join(VDIR, f), VARIANT=f[:-3])
                 r = subprocess.run([sys.executable, "-c", TIMER], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
-                print(r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "%s: no output (rc %d)" % (f, r.returncode), flush=True)
+                print(r.stdout.strip() if r.stdout.strip() else "%s: no output (rc %d)" % (f, r.returncode), flush=True)
 
 
 if __name__ == "__main__":
