@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdeepmod_b200.so")
-SOURCES = ["dm_api.cu", "dm_features.cu", "dm_hist.cu", "dm_lstm_fp32.cu", "dm_lstm_tc.cu", "dm_cluster.cu", "dm_align.cu", "dm_signal.cu", "dm_reduce.cu"]
+SOURCES = ["dm_api.cu", "dm_features.cu", "dm_hist.cu", "dm_lstm_fp32.cu", "dm_lstm_tc.cu", "dm_cluster.cu", "dm_align.cu", "dm_signal.cu", "dm_reduce.cu", "dm_synth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 

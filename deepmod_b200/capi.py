@@ -47,6 +47,11 @@ class DmSamBatch(C.Structure):
                 ("seq", _u8p)]
 
 
+class DmSynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("mean_len", C.c_float), ("len_lo", C.c_int32), ("len_hi", C.c_int32),
+                ("max_clip", C.c_int32), ("length_kind", C.c_int32)]
+
+
 class DmClusterWeights(C.Structure):
     _fields_ = [("w1", _fp), ("b1", _fp), ("w2", _fp), ("b2", _fp), ("wo", _fp), ("bo", _fp)]
 
@@ -88,6 +93,10 @@ SIGNATURES = {
                                      _i32p, _i32p, _fp, _fp, _i32p, _i64p]),
     "dm_write_cluster_bed": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(DmClusterWeights), C.c_int, C.c_char_p, C.c_char_p,
                                        _i64p]),
+    "dm_synth_describe": (C.c_int, [C.c_void_p, C.POINTER(DmSynthSpec), C.c_int64, C.c_int32, _i32p, _i32p]),
+    "dm_synth_generate": (C.c_int, [C.c_void_p, C.POINTER(DmSynthSpec), C.c_int64, C.c_int32, _i64p]),
+    "dm_resident_sizes": (C.c_int, [C.c_void_p, _i32p, _i64p, _i64p, _i64p]),
+    "dm_fetch_inputs": (C.c_int, [C.c_void_p, _i64p, _fp, _fp, _fp, _u8p, _i64p, _u8p, _u8p, _i64p, _i32p, _i32p, _i32p, _i8p]),
     "dm_detect_batch": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _fp, _u8p, _i32p]),
     "dm_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _i64p]),
     "dm_detect_resident": (C.c_int, [C.c_void_p, C.c_int]),
@@ -413,6 +422,45 @@ class Context(object):
         self._check(self.lib.dm_detect_batch(self._h, C.byref(pb.struct), _ptr(p1, C.c_float), _ptr(pred, C.c_uint8),
                                              _ptr(status, C.c_int32)), "dm_detect_batch")
         return p1, pred, status
+
+    # -- device-side synthetic reads (benchmark workload, BASELINE configs[2]) ----------------------
+    @staticmethod
+    def synth_spec(seed=2, mean_len=8000.0, len_lo=600, len_hi=60000, max_clip=30, length_kind="gamma"):
+        return DmSynthSpec(int(seed), float(mean_len), int(len_lo), int(len_hi), int(max_clip),
+                           {"gamma": 0, "loguniform": 1}[length_kind])
+
+    def synth_describe(self, spec, first_read, n_reads):
+        """-> (events per read, windows per read) of reads first_read .. first_read + n_reads - 1."""
+        ev, win = np.zeros(n_reads, np.int32), np.zeros(n_reads, np.int32)
+        self._check(self.lib.dm_synth_describe(self._h, C.byref(spec), int(first_read), int(n_reads), _ptr(ev, C.c_int32),
+                                               _ptr(win, C.c_int32)), "dm_synth_describe")
+        return ev, win
+
+    def synth_generate(self, spec, first_read, n_reads):
+        """Generate the reads into the resident batch; -> number of windows."""
+        n = C.c_int64()
+        self._check(self.lib.dm_synth_generate(self._h, C.byref(spec), int(first_read), int(n_reads), C.byref(n)), "dm_synth_generate")
+        return n.value
+
+    def resident_sizes(self):
+        r, e, c, w = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.dm_resident_sizes(self._h, C.byref(r), C.byref(e), C.byref(c), C.byref(w)), "dm_resident_sizes")
+        return r.value, e.value, c.value, w.value
+
+    def fetch_inputs(self, alloc=None):
+        """The resident batch as a packed-batch dict of host arrays (``alloc(shape, dtype)`` may hand out pinned memory)."""
+        alloc = alloc or (lambda shape, dt: np.zeros(shape, dt))
+        n, ne, nc, _ = self.resident_sizes()
+        out = {k: alloc((m,), dt) for k, dt, m in (
+            ("ev_off", np.int64, n + 1), ("ev_mean", np.float32, ne), ("ev_stdv", np.float32, ne), ("ev_len", np.float32, ne),
+            ("ev_base", np.uint8, ne), ("col_off", np.int64, n + 1), ("col_refbase", np.uint8, nc), ("col_readbase", np.uint8, nc),
+            ("col_refpos", np.int64, nc), ("start_clip", np.int32, n), ("end_clip", np.int32, n), ("contig", np.int32, n),
+            ("strand", np.int8, n))}
+        ct = {np.int64: C.c_int64, np.float32: C.c_float, np.uint8: C.c_uint8, np.int32: C.c_int32, np.int8: C.c_int8}
+        order = ("ev_off", "ev_mean", "ev_stdv", "ev_len", "ev_base", "col_off", "col_refbase", "col_readbase", "col_refpos",
+                 "start_clip", "end_clip", "contig", "strand")
+        self._check(self.lib.dm_fetch_inputs(self._h, *[_ptr(out[k], ct[out[k].dtype.type]) for k in order]), "dm_fetch_inputs")
+        return out
 
     def set_pipeline(self, parts):
         """Sub-batch pipelining of detect_batch: 0 = by batch size, 1 = off, n = always n read ranges."""

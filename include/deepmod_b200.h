@@ -245,6 +245,28 @@ int dm_align_upload(dm_ctx* ctx, const dm_sam_batch* sb, int64_t* n_windows, int
 int dm_fetch_alignment(dm_ctx* ctx, int64_t* col_off, uint8_t* refbase, uint8_t* readbase, int64_t* refpos,
                        int32_t* start_clip, int32_t* end_clip);
 
+/* ---- synthetic reads generated on the device (benchmark workload: SURVEY 8(d) row 2, BASELINE configs[2]) ------ */
+/* Read `id` of the set is a pure function of (seed, id): Philox4x32-10 counters; length ~ Gamma(2, mean_len / 2) clipped to
+ * [len_lo, len_hi], clips ~ U{0..max_clip}, all-match alignment on the contigs of dm_set_genome (iid ACGT genome, also a
+ * function of the seed), one event per base with the distributions of deepmod_b200/synth.py.  Any GPU can generate any
+ * range of ids, so one read set shards over 1..8 GPUs and must reduce to the same accumulator. */
+typedef struct dm_synth_spec {
+  uint64_t seed;
+  float    mean_len;
+  int32_t  len_lo, len_hi, max_clip;
+  int32_t  length_kind;   /* 0: Gamma(2, mean_len / 2) clipped to [len_lo, len_hi]; 1: log-uniform in [len_lo, len_hi] (configs[3]) */
+} dm_synth_spec;
+/* Events and windows of reads first_read .. first_read + n_reads - 1 (for cutting ranges balanced by mapped bases). */
+int dm_synth_describe(dm_ctx* ctx, const dm_synth_spec* spec, int64_t first_read, int32_t n_reads,
+                      int32_t* n_events_out, int32_t* n_windows_out);
+/* Generate those reads straight into the resident batch, as dm_batch_upload would leave it. */
+int dm_synth_generate(dm_ctx* ctx, const dm_synth_spec* spec, int64_t first_read, int32_t n_reads, int64_t* n_windows);
+/* Sizes and input arrays of the resident batch (to host buffers sized by dm_resident_sizes; any pointer may be NULL). */
+int dm_resident_sizes(dm_ctx* ctx, int32_t* n_reads, int64_t* n_events, int64_t* n_cols, int64_t* n_windows);
+int dm_fetch_inputs(dm_ctx* ctx, int64_t* ev_off, float* ev_mean, float* ev_stdv, float* ev_len, uint8_t* ev_base,
+                    int64_t* col_off, uint8_t* col_refbase, uint8_t* col_readbase, int64_t* col_refpos,
+                    int32_t* start_clip, int32_t* end_clip, int32_t* contig, int8_t* strand);
+
 /* Same work with the batch resident in HBM: upload once, run many times. */
 int dm_batch_upload(dm_ctx* ctx, const dm_batch* b, int64_t* n_windows);
 int dm_detect_resident(dm_ctx* ctx, int accumulate /* 0: skip the histogram update */);

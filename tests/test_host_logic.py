@@ -124,21 +124,102 @@ def test_filter_reads_region_and_conunk(batch):
         assert b["contig"][r] == 0 and b["col_refpos"][c0:c1].min() > 10000
 
 
-def test_bench_rank_shards_hold_equal_window_counts():
-    """bench.py at N > 1: every rank generates its own reads and cuts them to rank 0's window count
-    (the job's sharding rule: contiguous read ranges balanced by sum(Lmap))."""
+def _load_bench():
     import importlib.util
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     spec = importlib.util.spec_from_file_location("dm_bench", os.path.join(root, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    base = bench.make_workload(0, 12)
-    target = int(synth.n_windows(base).sum())
-    for rank in (1, 5):
-        mine = bench.make_workload(rank, 12, target)
-        got = int(synth.n_windows(mine).sum())
-        longest = int(synth.n_windows(mine).max())
-        assert got <= target and target - got <= 60000          # within one (clipped-length) read
-        assert not np.array_equal(mine["ev_mean"][:100], base["ev_mean"][:100])      # its own reads
-        capi.PackedBatch(mine)                                   # still a valid packed batch
-        assert longest > 0
+    return bench
+
+
+def test_bench_strong_scaling_cuts_partition_every_step():
+    """bench.py at N > 1: the SAME reads of a step are cut into N contiguous ranges balanced by mapped bases
+    (the job's sharding rule) -- a partition, identical on every rank, same rule as shard_by_windows."""
+    bench = _load_bench()
+    rng = np.random.default_rng(3)
+    win = np.clip(rng.gamma(2.0, 4000.0, 6250), 600, 60000).astype(np.int32)
+    for world in (1, 2, 4, 8):
+        cuts = bench.balanced_cuts(win, world)
+        assert len(cuts) == world and cuts[0][0] == 0 and cuts[-1][1] == len(win)
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        per = np.array([int(win[lo:hi].sum()) for lo, hi in cuts])
+        assert per.max() - per.min() <= 2 * 60000 and per.sum() == int(win.sum())
+        want = synth.shard_by_windows({"ev_off": np.concatenate([[0], np.cumsum(win)]).astype(np.int64),
+                                       "start_clip": np.zeros(len(win), np.int32), "end_clip": np.zeros(len(win), np.int32)}, world)
+        assert [(int(w[0]), int(w[-1]) + 1) for w in want] == cuts
+
+
+def test_cpu_baseline_sample_is_the_benchmark_distribution():
+    bench = _load_bench()
+    shards, n = bench.cpu_sample(3, 2)
+    assert len(shards) == 3 and all(len(s["start_clip"]) == 2 for s in shards)
+    assert n == sum(int(synth.n_windows(s).sum()) for s in shards)
+    for s in shards:                                    # all-match alignments: one column per mapped event
+        assert np.array_equal(np.diff(s["col_off"]), synth.n_windows(s))
+        assert not (s["col_readbase"] == ord("-")).any() and np.array_equal(s["col_refbase"], s["col_readbase"])
+
+
+def test_vectorised_read_filters_equal_the_per_read_loop(batch):
+    """filter_reads against a direct restatement of handle_record's tests (myDetect.py:502, :548-559)."""
+    b, _ = batch
+    names = ["chr1", "chr_un"]
+    lmap = synth.n_windows(b)
+
+    def loop(mo):
+        keep = []
+        for r in range(len(lmap)):
+            name = names[int(b["contig"][r])]
+            if (not mo["ConUnk"]) and any(ch in name for ch in "_-/:"):
+                continue
+            c0, c1 = int(b["col_off"][r]), int(b["col_off"][r + 1])
+            pos = int(b["col_refpos"][c0:c1].min())
+            if any(cr[0] in ("", None, name) and (cr[1] in ("", None) or pos > cr[1]) and
+                   (cr[2] in ("", None) or pos + int(lmap[r]) < cr[2]) for cr in mo["region"]):
+                keep.append(r)
+        return keep
+    for mo in ({"region": [["chr1", 10000, 30000]], "ConUnk": True}, {"region": [["chr1", None, 20000], ["chr_un", 5000, None]], "ConUnk": True},
+               {"region": [[None, 2000, None]], "ConUnk": False}, {"region": [["nope", None, None]], "ConUnk": True}):
+        assert list(detect.filter_reads(b, names, mo)) == loop(mo)
+    # the optional pre-trim fields take precedence (pos / len(m_event) before the first/last-match trimming)
+    b2 = dict(b, aln_pos=np.full(len(lmap), 50, np.int64), aln_events=np.full(len(lmap), 10, np.int64))
+    assert len(detect.filter_reads(b2, names, {"region": [[None, 49, 61]], "ConUnk": True})) == len(lmap)
+    assert len(detect.filter_reads(b2, names, {"region": [[None, 50, None]], "ConUnk": True})) == 0
+
+
+def test_take_reads_gather_equals_concatenation(batch):
+    b, _ = batch
+    idx = np.array([7, 2, 2, 30, 11])
+    got = synth.take_reads(b, idx)
+    for k, off in (("ev_mean", "ev_off"), ("ev_base", "ev_off"), ("col_refpos", "col_off"), ("col_readbase", "col_off")):
+        want = np.concatenate([b[k][int(b[off][r]):int(b[off][r + 1])] for r in idx])
+        assert np.array_equal(got[k], want)
+    assert np.array_equal(got["strand"], b["strand"][idx]) and got["ev_off"][-1] == len(got["ev_mean"])
+    view = synth.take_reads(b, np.arange(4, 9))                       # contiguous: views, no copy
+    assert view["ev_mean"].base is not None and np.array_equal(view["ev_off"], b["ev_off"][4:10] - b["ev_off"][4])
+    no_base = {k: v for k, v in b.items() if k != "ev_base"}            # ev_base is optional everywhere
+    assert "ev_base" not in synth.take_reads(no_base, idx) and "ev_base" not in synth.slice_reads(no_base, 1, 3)
+
+
+def test_plan_files_and_prefetcher(tmp_path):
+    files = []
+    for i, size in enumerate((500, 100, 400, 300, 200)):
+        p = tmp_path / ("f%d.dmreads.npz" % i)
+        p.write_bytes(b"x" * size)
+        files.append(str(p))
+    assert detect.plan_files(files, 1, 0) == (files, False)
+    assert detect.plan_files(files[:2], 4, 3) == (files[:2], True)      # fewer files than ranks: shard inside the files
+    shares = [detect.plan_files(files, 2, r) for r in range(2)]
+    assert not shares[0][1] and sorted(shares[0][0] + shares[1][0]) == files and not set(shares[0][0]) & set(shares[1][0])
+    load = [sum(os.path.getsize(f) for f in s[0]) for s in shares]
+    assert abs(load[0] - load[1]) <= 100
+    seen = [(it, v) for it, v in detect.Prefetcher(range(5), lambda x: x * x)]
+    assert seen == [(i, i * i) for i in range(5)]
+
+    def boom(x):
+        if x == 2:
+            raise ValueError("bad file")
+        return x
+    with pytest.raises(ValueError, match="bad file"):
+        for _ in detect.Prefetcher(range(5), boom):
+            pass
