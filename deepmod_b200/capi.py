@@ -101,6 +101,8 @@ SIGNATURES = {
     "dm_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _i64p]),
     "dm_detect_resident": (C.c_int, [C.c_void_p, C.c_int]),
     "dm_set_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
+    "dm_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "dm_pinned_free": (None, [C.c_void_p]),
     "dm_fetch_results": (C.c_int, [C.c_void_p, _fp, _u8p, _i32p]),
     "dm_build_windows": (C.c_int, [C.c_void_p, _fp]),
     "dm_launch_count": (C.c_int64, [C.c_void_p]),
@@ -185,6 +187,57 @@ class PackedBatch(object):
 
     def nbytes(self):
         return sum(v.nbytes for v in self.a.values() if v is not None)
+
+
+class PinnedArena(object):
+    """One page-locked host buffer handing out numpy arrays (bump allocation, 256-byte aligned); ``reset()`` makes the
+    whole buffer available again.  Grows (re-allocates) when a request does not fit -- never while arrays of the
+    current round are alive, because a round starts with ``reset(need)``."""
+
+    def __init__(self, nbytes=0):
+        self.lib = load_library()
+        self.ptr, self.size, self.used = C.c_void_p(), 0, 0
+        self.overflow = []                      # pageable arrays handed out when the buffer was too small
+        if nbytes:
+            self._grow(nbytes)
+
+    def _grow(self, nbytes):
+        self.close()
+        p = C.c_void_p()
+        rc = self.lib.dm_pinned_alloc(int(nbytes), C.byref(p))
+        if rc != 0:
+            msg = self.lib.dm_last_error(None)
+            raise DeepModError("dm_pinned_alloc failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+        self.ptr, self.size, self.used = p, int(nbytes), 0
+        self._buf = (C.c_uint8 * self.size).from_address(p.value)
+
+    def reset(self, need=0):
+        self.used, self.overflow = 0, []
+        if need > self.size:
+            self._grow(need + need // 8)
+
+    def alloc(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        start = (self.used + 255) // 256 * 256
+        if start + n > self.size:
+            a = np.empty(shape, dtype)
+            self.overflow.append(a)
+            return a
+        self.used = start + n
+        return np.frombuffer(self._buf, dtype=dtype, count=int(np.prod(shape)), offset=start).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self._buf = None
+            self.lib.dm_pinned_free(self.ptr)
+            self.ptr, self.size = C.c_void_p(), 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def reduce_unique_id():

@@ -532,6 +532,20 @@ int detect_batch_pipelined(dm_ctx* ctx, const dm_batch* hb, int parts, float* p1
 
 extern "C" {
 
+// page-locked host memory for callers that stage their input files themselves (a loader thread reading
+// file k+1 into one of these while dm_detect_batch works on file k): copies from it are truly asynchronous
+int dm_pinned_alloc(size_t bytes, void** out) {
+  if (!out) return DM_ERR_ARG;
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) { dm_set_error(nullptr, std::string("dm_pinned_alloc: ") + cudaGetErrorString(e)); return DM_ERR_CUDA; }
+  return DM_OK;
+}
+
+void dm_pinned_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 int dm_set_pipeline(dm_ctx* ctx, int parts) {
   if (!ctx) return DM_ERR_ARG;
   if (parts < 0 || parts > 64) return fail(ctx, DM_ERR_ARG, "dm_set_pipeline: parts must be in [0, 64]");

@@ -171,10 +171,12 @@ class Prefetcher(object):
                 pass
 
 
-def load_packed(path, contig_names, moptions, shard=None):
+def load_packed(path, contig_names, moptions, shard=None, arena=None):
     """One input file -> list of ``PackedBatch`` ready for ``dm_detect_batch`` (filters and sharding applied),
-    with the index of their first read in the file."""
-    batch, names, _ = reads_io.load_reads(path)
+    with the index of their first read in the file.  ``arena``: page-locked memory the arrays are read into."""
+    if arena is not None:
+        arena.reset(os.path.getsize(path) + 65536)
+    batch, names, _ = reads_io.load_reads(path, alloc=arena.alloc if arena is not None else None)
     if list(names) != list(contig_names):
         raise capi.DeepModError("%s was packed against a different contig table" % path)
     first = np.arange(len(batch["start_clip"]), dtype=np.int64)
@@ -199,7 +201,10 @@ def detect_handler(moptions, ctx, read_files, contig_names, failed, shard=None, 
     ``predetail.DetailWriter``) receives the per-read predictions when the per-read output is wanted (:716-782).
     Returns (reads seen, windows predicted)."""
     n_reads = n_windows = 0
-    pre = Prefetcher(read_files, lambda p: load_packed(p, contig_names, moptions, shard))
+    # three page-locked arenas in rotation: one under the GPU call, one queued, one being filled (Prefetcher depth 1)
+    arenas = [capi.PinnedArena() for _ in range(3)]
+    order = {p: i for i, p in enumerate(read_files)}
+    pre = Prefetcher(read_files, lambda p: load_packed(p, contig_names, moptions, shard, arenas[order[p] % 3]), depth=1)
     try:
         for path, parts in pre:
             for pb, first in parts:
@@ -216,6 +221,8 @@ def detect_handler(moptions, ctx, read_files, contig_names, failed, shard=None, 
                     detail.add_batch(path, first, pb, pred, status, contig_names)
     finally:
         pre.close()
+        for a in arenas:
+            a.close()
     return n_reads, n_windows
 
 
@@ -389,6 +396,8 @@ def mDetect_manager(moptions):
         detail = None
         try:
             ctx.set_genome(contig_len, moptions["Base"])
+            timing["init_s"] = time.time() - start_time          # file discovery, model load, CUDA context, accumulator
+            t_pred = time.time()
             if moptions.get("saveDetail", 0):
                 from . import predetail
                 detail = predetail.DetailWriter(out_dir, moptions["wrkBase"], rank, contig_len)
@@ -405,7 +414,7 @@ def mDetect_manager(moptions):
                 detail.close()
         except Exception as e:                      # every rank must reach the exchange below, or the others hang in it
             error = "%s: %s" % (type(e).__name__, e)
-        timing["predict_s"] = time.time() - start_time
+        timing["predict_s"] = time.time() - (t_pred if "init_s" in timing else start_time)
         # one small object per rank: failure, rejected reads, counts (rank 0 used to report only its own)
         reports = ranks.gather((error, failed, n_reads, n_windows))
         errors = ["rank %d: %s" % (i, r[0]) for i, r in enumerate(reports) if r[0]]
@@ -435,7 +444,7 @@ def mDetect_manager(moptions):
             timing["summary_s"] = time.time() - t1
             print("Genomic-position Detection consuming time %d" % (time.time() - t1))
             if out_level <= OUTPUT_INFO:
-                print("reads=%d bases=%d (%.4g bases/s in the prediction phase) beds=%d %s" % (
+                print("reads=%d bases=%d (%.4g bases/s files -> accumulator) beds=%d %s" % (
                     n_reads, n_windows, n_windows / max(timing["predict_s"], 1e-9), len(written), timing))
             with open(out_dir + ".done", "a"):                                      # :1263
                 os.utime(out_dir + ".done", None)

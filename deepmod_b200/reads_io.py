@@ -25,15 +25,55 @@ def save_reads(path, batch, contig_names, contig_len):
         np.savez(fh, **arrays)
 
 
-def load_reads(path, header_only=False):
-    """-> (batch dict or None, contig names, contig lengths)"""
-    with np.load(path, allow_pickle=False) as z:
-        names = [str(x) for x in z["contig_names"]]
-        lens = z["contig_len"].astype(np.int64)
-        if header_only:
-            return None, names, lens
-        batch = {k: z[k] for k in BATCH_KEYS if k in z.files}
-    return batch, names, lens
+def _read_stored_npz(path, want, alloc=None):
+    """Arrays of an UNCOMPRESSED .npz (what ``np.savez`` writes) read straight from their byte ranges in the file --
+    one ``readinto`` per array instead of zipfile's chunked read + CRC pass, which caps ``np.load`` at ~1 GB/s
+    while a B200 consumes ~2.5 GB/s of packed reads.  -> dict, or None when the file is not laid out that way."""
+    import struct
+    import zipfile
+    out = {}
+    with zipfile.ZipFile(path) as zf, open(path, "rb") as fh:
+        for info in zf.infolist():
+            name = info.filename[:-4] if info.filename.endswith(".npy") else info.filename
+            if want is not None and name not in want:
+                continue
+            if info.compress_type != zipfile.ZIP_STORED:
+                return None
+            fh.seek(info.header_offset)
+            hdr = fh.read(30)
+            if len(hdr) != 30 or hdr[:4] != b"PK\x03\x04":
+                return None
+            n_name, n_extra = struct.unpack("<HH", hdr[26:30])
+            fh.seek(info.header_offset + 30 + n_name + n_extra)
+            version = np.lib.format.read_magic(fh)
+            if version == (1, 0):
+                shape, fortran, dtype = np.lib.format.read_array_header_1_0(fh)
+            elif version == (2, 0):
+                shape, fortran, dtype = np.lib.format.read_array_header_2_0(fh)
+            else:
+                return None
+            if dtype.hasobject or fortran:
+                return None
+            arr = alloc(shape, dtype) if alloc is not None else np.empty(shape, dtype)
+            if arr.nbytes and fh.readinto(memoryview(arr.reshape(-1)).cast("B")) != arr.nbytes:
+                raise IOError("%s: member %s is truncated" % (path, info.filename))
+            out[name] = arr
+    return out
+
+
+def load_reads(path, header_only=False, alloc=None):
+    """-> (batch dict or None, contig names, contig lengths).  ``alloc(shape, dtype)`` may supply the arrays' memory
+    (e.g. a ``capi.PinnedArena``)."""
+    want = ("contig_names", "contig_len") if header_only else BATCH_KEYS + ("contig_names", "contig_len")
+    z = _read_stored_npz(path, set(want), None if header_only else alloc)
+    if z is None:                                    # compressed or unusual file: numpy's own reader
+        with np.load(path, allow_pickle=False) as f:
+            z = {k: f[k] for k in want if k in f.files}
+    names = [str(x) for x in z["contig_names"]]
+    lens = z["contig_len"].astype(np.int64)
+    if header_only:
+        return None, names, lens
+    return {k: z[k] for k in BATCH_KEYS if k in z}, names, lens
 
 
 # ---------------------------------------------------------------------------------------------------

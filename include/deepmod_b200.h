@@ -193,6 +193,10 @@ int dm_write_cluster_bed(dm_ctx* ctx, int32_t contig, const dm_cluster_weights* 
  * status_out[n_reads] receives dm_read_status.  Any output may be NULL. */
 int dm_detect_batch(dm_ctx* ctx, const dm_batch* b, float* p1_out, uint8_t* pred_out,
                     int32_t* status_out);
+/* Page-locked host memory for input staging (optional: dm_detect_batch takes any host pointer; from these buffers its
+ * copies overlap the kernels without a driver-side staging pass). */
+int  dm_pinned_alloc(size_t bytes, void** out);
+void dm_pinned_free(void* p);
 /* dm_detect_batch cuts a large batch into contiguous read ranges and alternates them between two
  * device slots / streams, so the host<->device copies of one range run under the kernels of the
  * other (results are identical: reads are independent, the accumulator is a sum).  parts: 0 = decide

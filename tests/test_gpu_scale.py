@@ -60,9 +60,10 @@ def test_full_size_batch_properties():
     assert total_mod == want_mod
     # the two tensor-core variants are the same arithmetic: bit-identical results
     assert np.array_equal(res[capi.BF16][0], res[capi.BF16_1CTA][0])
-    # tensor-core arithmetic vs fp32, gated at <= 2x the measured values (round 2, B200, ~0.9 M windows:
-    # fp16 operands flip rate 1.5e-4 / mean |dp1| 2.6e-4; bf16 operands 3.9e-4 / 5.5e-4)
-    for prec, name, max_flips, max_mean, max_err in ((capi.F16, "f16", 4e-4, 6e-4, 0.12), (capi.BF16, "bf16", 8e-4, 1.1e-3, 0.2)):
+    # tensor-core arithmetic vs fp32, gated at <= 2x the measured values (round 2, B200, 835 853 windows:
+    # fp16 operands flip rate 2.4e-4 / mean |dp1| 2.79e-4 / max 0.011, mod differs on 71 of 172 840 BED rows;
+    # bf16 operands 4.0e-4 / 5.72e-4 / 0.038, 130 rows)
+    for prec, name, max_flips, max_mean, max_err in ((capi.F16, "f16", 5e-4, 5.6e-4, 0.05), (capi.BF16, "bf16", 8e-4, 1.1e-3, 0.15)):
         flips = float(np.mean(res[prec][1][ok_w] != pred[ok_w]))
         err = np.abs(res[prec][0][ok_w] - p1[ok_w])
         mod_fp32 = sum(int(h[2].sum()) for h in hist.values())
