@@ -362,6 +362,7 @@ def hg38_leg(local, rank, world, ranks_bcast, ranks_gather, pk):
         hg.reduce_comm(uid, rank, world)                # first call: communicator set-up + the sum
         # a second sum of the (already merged) accumulator is the steady-state cost of the exchange at this size
         ms = hg.reduce_comm(None, rank, world)
+        hg.reduce_finalize()                            # collective, while every rank is here (rank 0 goes on alone below)
         after = hg.hist_totals()
         tot = torch.tensor([before[0], before[1]], dtype=torch.int64, device="cuda")
         torch.distributed.all_reduce(tot)
@@ -559,6 +560,7 @@ def main():
         e2e_bases += int(h.n_windows_per_read[st == 0].sum())
     if world > 1:
         ctx.reduce_comm(None, rank, world)
+        ctx.reduce_finalize()                           # last exchange of this context: collective communicator teardown
     barrier()
     dt_e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
     eb = torch.tensor([float(e2e_bases)], device="cuda", dtype=torch.float64)
@@ -580,6 +582,7 @@ def main():
         barrier()
 
     if rank != 0:
+        ctx.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()

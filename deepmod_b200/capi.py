@@ -76,6 +76,7 @@ SIGNATURES = {
     "dm_reduce": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "dm_reduce_unique_id": (C.c_int, [_u8p]),
     "dm_reduce_comm": (C.c_int, [C.c_void_p, _u8p, C.c_int, C.c_int]),
+    "dm_reduce_finalize": (C.c_int, [C.c_void_p]),
     "dm_hist_merge": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dm_hist_totals": (C.c_int, [C.c_void_p, _u64p, _u64p, _u64p, _u64p]),
     "dm_last_reduce_ms": (C.c_int, [C.c_void_p, _fp]),
@@ -382,6 +383,10 @@ class Context(object):
         ms = C.c_float()
         self._check(self.lib.dm_last_reduce_ms(self._h, C.byref(ms)), "dm_last_reduce_ms")
         return ms.value
+
+    def reduce_finalize(self):
+        """Collective: every rank calls it after its last ``reduce_comm`` (destroys the NCCL communicator)."""
+        self._check(self.lib.dm_reduce_finalize(self._h), "dm_reduce_finalize")
 
     def hist_nonzero(self, contig, strand):
         n = C.c_int64()

@@ -197,6 +197,13 @@ int dm_reduce(dm_ctx** ctxs, int n) {
   return rc;
 }
 
+int dm_reduce_finalize(dm_ctx* ctx) {
+  if (!ctx) return DM_ERR_ARG;
+  if (ctx->stream) DM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  dm_reduce_release(ctx);
+  return DM_OK;
+}
+
 int dm_last_reduce_ms(const dm_ctx* ctx, float* ms) {
   if (!ctx || !ms) return DM_ERR_ARG;
   *ms = ctx->reduce_ms;

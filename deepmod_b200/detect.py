@@ -428,6 +428,7 @@ def mDetect_manager(moptions):
         n_reads, n_windows = sum(r[2] for r in reports), sum(r[3] for r in reports)
         if world > 1:
             timing["reduce_ms"] = ctx.reduce_comm(uid, rank, world)      # the one exchange step of the job
+            ctx.reduce_finalize()                                        # collective: all ranks are here together
         pred_time = time.time() - start_time
         if rank == 0:
             if detail is not None:

@@ -135,6 +135,10 @@ int dm_reduce(dm_ctx** ctxs, int n);
  * context: later calls may pass id == NULL. */
 int dm_reduce_unique_id(uint8_t id_out[128]);
 int dm_reduce_comm(dm_ctx* ctx, const uint8_t* id, int rank, int n_ranks);
+/* Destroys the communicator dm_reduce_comm keeps in the context.  ncclCommDestroy is a COLLECTIVE: it returns once every
+ * rank has called it, so call this on all ranks together, right after the last exchange (dm_destroy does it too: a
+ * rank that destroys its context early waits here for the others; a rank that never does leaves them waiting). */
+int dm_reduce_finalize(dm_ctx* ctx);
 /* dst += src for two contexts of ONE process holding the same genome (same or different GPU of the box): counters
  * add, key-created flags OR -- the merge of DeepMod_tools/sum_chr_mod.py:47-52 without going through BED files. */
 int dm_hist_merge(dm_ctx* dst, dm_ctx* src);
