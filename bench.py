@@ -560,9 +560,10 @@ def main():
         e2e_bases += int(h.n_windows_per_read[st == 0].sum())
     if world > 1:
         ctx.reduce_comm(None, rank, world)
-        ctx.reduce_finalize()                           # last exchange of this context: collective communicator teardown
     barrier()
     dt_e = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    if world > 1:
+        ctx.reduce_finalize()                           # last exchange of this context: collective communicator teardown
     eb = torch.tensor([float(e2e_bases)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt_e, op=dist.ReduceOp.MAX)
