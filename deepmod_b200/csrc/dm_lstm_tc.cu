@@ -43,7 +43,14 @@ constexpr int TC_EPI_THREADS = TC_EPI_WARPS * 32;
 constexpr int TC_THREADS = (TC_CTRL_WARPS + TC_EPI_WARPS) * 32;
 constexpr int TC_CHUNK_N = 80;          // gate columns per MMA and TMEM slot
 constexpr int TC_NCHUNK = 5;
-constexpr int TC_TSLOTS = 6;
+#ifndef TC_TSLOTS_N
+#define TC_TSLOTS_N 5      // accumulator ring depth (slots of 80 TMEM columns).  5 = one slot per N-chunk of a cell-step: slot
+                           // indices, TMEM addresses and barrier addresses become compile-time constants in the unrolled
+                           // chunk loops (less uniform-datapath bookkeeping), at the price of one slot of run-ahead:
+                           // 5 is 1.7 % faster than 6 (profiles/r02_variants_sweep2.txt)
+#endif
+constexpr int TC_TSLOTS = TC_TSLOTS_N;
+constexpr bool TC_STATIC_SLOTS = TC_TSLOTS == 5;          // == TC_NCHUNK (defined below)
 constexpr int TC_ACOL = 2048;           // A core column: 128 rows x 16 B
 constexpr int TC_HCOLS = 13;            // 100 units + 4 extra K slots
 constexpr int TC_HTILE = TC_HCOLS * TC_ACOL;
@@ -60,6 +67,34 @@ __host__ __device__ constexpr int tc_unit0(int j, int s);
 #endif
 #ifndef TC_UNIWARP
 #define TC_UNIWARP 1       // warp index through a shuffle (provably warp-uniform for the compiler)
+#endif
+#ifndef TC_GATE32
+#define TC_GATE32 1        // 1: the four gate tanh are taken in f32 straight from the accumulator registers and their RESULTS
+                           //    are packed to f16x2 (8 MUFU.TANH + 4 F2FP per unit pair instead of 4 F2FP + 8 MUFU.TANH.F16 + 4 PRMT):
+                           //    same speed, the gate inputs keep their fp32 precision (mean |dp1| 1.6e-4 instead of 2.8e-4)
+#endif
+#ifndef TC_FMAF
+#define TC_FMAF 0          // 1: the forget gate's sigmoid is evaluated on the FMA / ALU pipes in packed fp16 (exponent arithmetic
+                           //    + two small polynomials, |error| <= 1.0e-3) instead of on the MUFU pipe, which binds this kernel:
+                           //    16 instead of 20 MUFU per unit quad.  The f-gate weight columns are then scaled by log2(e)
+                           //    instead of 0.5.  tools/numerics_study.py: no measurable change of |dp1| (gates i and f tolerate it).
+                           //    MEASURED (profiles/r02_variants_sweep3.txt, r02_fma_offload_ncu.txt): the MUFU pipe drops from 86 % to
+                           //    67 % busy and the kernel is NOT faster (-3 % with TC_PARK, -10 % without: spills): 35 % more
+                           //    instructions put the issue slots at 67 %, with six warps per scheduler that is the new limit.  Off.
+#endif
+#ifndef TC_FMAI
+#define TC_FMAI 0          // 1: the same for the input gate's sigmoid (12 MUFU per unit quad; measure before use: the FMA pipe
+                           //    then carries about as much as the MUFU pipe)
+#endif
+#ifndef TC_SETMAXNREG
+#define TC_SETMAXNREG 0    // 1: the control warpgroup (warps 20..23) shrinks to 40 registers per thread and the five epilogue
+                           //    warpgroups grow to 88 (640 x 88 + 128 x 40 = 768 x 80, the launch allocation)
+#endif
+#ifndef TC_PARK
+#define TC_PARK 0          // 1: only the cell state of the layer being stepped lives in registers (10 per thread); the other two
+                           //    layers' states are parked in the 112 TMEM columns the 5-slot accumulator ring leaves free
+                           //    (tcgen05.st / tcgen05.ld once per cell-step).  20 registers back: no spills in the chunk loops,
+                           //    but the swap at every step start costs more than the spills did (-2.7 %).  Off.
 #endif
 #ifndef TC_EARLYLD
 #define TC_EARLYLD 0       // when the next chunk's accumulator load is issued (its 16 registers are free as soon as the
@@ -188,6 +223,17 @@ __device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t* v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld2(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tc_st2(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(v[0]), "r"(v[1]) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // same, with the loaded registers as in/out operands: no consumer of v can be scheduled above the wait
 __device__ __forceinline__ void tc_wait_ld16(uint32_t (&v)[16]) {
@@ -266,11 +312,37 @@ __host__ __device__ constexpr uint32_t umma_idesc(int m, int n, bool f16 = false
   return (1u << 4) | (f16 ? 0u : (1u << 7) | (1u << 10)) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
-// one MUFU, two results
+__device__ __forceinline__ float tanh32_mufu(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two results per PTX instruction - but two MUFU.TANH.F16 + one PRMT in SASS (there is no packed MUFU on sm_100)
 __device__ __forceinline__ __half2 tanh2_mufu(__half2 x) {
   uint32_t y;
   asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(*reinterpret_cast<const uint32_t*>(&x)));
   return *reinterpret_cast<__half2*>(&y);
+}
+// sigmoid(x) for two values at once, WITHOUT the MUFU pipe.  u = x * log2(e) (the GEMM delivers it: weight scaling).
+//   a = min(|u|, 14.5);  r = round(a) by the mantissa trick (1039 - a has an ulp of 1);  e = 2^-a = 2^-(a - r) * 2^-r:
+//   a quadratic in the fraction times an exponent built from the low bits of (1039 - a);  1 / (1 + e) - 1/2 as a quartic in
+//   e on [0, 1];  the sign of u goes back on.  12 FMA-pipe + 5 ALU-pipe instructions for two results; max error 1.0e-3.
+__device__ __forceinline__ __half2 sigmoid2_fma(__half2 u) {
+  const __half2 kM = __floats2half2_rn(1039.f, 1039.f), kA = __floats2half2_rn(14.5f, 14.5f);
+  const __half2 a = __hmin2(__habs2(u), kA);
+  const __half2 tm = __hsub2(kM, a);
+  const __half2 fr = __hadd2(a, __hsub2(tm, kM));                    // a - round(a), in [-0.5, 0.5]
+  // 2^-fr  (fp16-rounded least-squares coefficients on Chebyshev nodes)
+  __half2 p = __hfma2(__floats2half2_rn(0.24267578f, 0.24267578f), fr, __floats2half2_rn(-0.7036133f, -0.7036133f));
+  p = __hfma2(p, fr, __floats2half2_rn(1.f, 1.f));
+  const uint32_t sbits = (*reinterpret_cast<const uint32_t*>(&tm) << 10) & 0x7C007C00u;      // 2^-round(a) (0 when round(a) = 15)
+  const __half2 e = __hmul2(p, *reinterpret_cast<const __half2*>(&sbits));
+  __half2 q = __hfma2(__floats2half2_rn(0.15686035f, 0.15686035f), e, __floats2half2_rn(-0.54248047f, -0.54248047f));
+  q = __hfma2(q, e, __floats2half2_rn(0.8720703f, 0.8720703f));
+  q = __hfma2(q, e, __floats2half2_rn(-0.9863281f, -0.9863281f));
+  q = __hfma2(q, e, __floats2half2_rn(0.49975586f, 0.49975586f));   // 1 / (1 + e) - 1/2 >= 0
+  const uint32_t sq = (*reinterpret_cast<const uint32_t*>(&u) & 0x80008000u) | *reinterpret_cast<const uint32_t*>(&q);
+  return __hadd2(__floats2half2_rn(0.5f, 0.5f), *reinterpret_cast<const __half2*>(&sq));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
@@ -416,6 +488,10 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
   if (PAIR) cluster_sync_all();       // both CTAs' barriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+#if TC_SETMAXNREG
+  if (warp >= TC_EPI_WARPS) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 88;");
+#endif
 
 // walks the 66 cell-steps in wavefront order; BODY sees dir, d, l, t, g
 #if TC_INTERLEAVE
@@ -478,6 +554,7 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
       } else if (warp == W_MMA) {               // "my epilogue has drained accumulator slot"
         uint32_t tslot = 0, tuse = 0;
         FOR_EACH_STEP({
+          if (TC_STATIC_SLOTS) tslot = 0;
           for (int j = 0; j < TC_NCHUNK; ++j) {
             mbar_wait(bar0 + 8 * (BAR_TEMPTY + tslot), tuse & 1);
             mbar_arrive_remote(bar0 + 8 * (BAR_TEMPTY + tslot), 0);
@@ -506,6 +583,8 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
       constexpr uint32_t b_step = (2 * G::BCOL) >> 4;                // two K core columns per MMA
       uint32_t slot = 0, use = 0, tslot = 0, tuse = 0, c = 0;
       FOR_EACH_STEP({
+        if (TC_STATIC_SLOTS) tslot = 0;                       // (it is 0 already: said so for constant folding)
+        if (G::NSTAGE == TC_NCHUNK) slot = 0;
         if (mine == 0 && lane == 0) TS(g * 8 + 0);
         // inputs of this cell-step were written by the epilogues of steps <= g-2, or g-1 in the
         // fill/drain corners of the wavefront (and across the direction switch)
@@ -576,7 +655,16 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
     }
   } else if (warp < TC_EPI_WARPS) {
     // ================= epilogue: gates -> (c, h) =================
+#if TC_PARK
+    static_assert(TC_STATIC_SLOTS && TC_INTERLEAVE && TC_T0SKIP, "TC_PARK needs the 5-slot ring (free TMEM columns), the interleaved order and the t = 0 shortcut");
+    __half2 cst[1][TC_NCHUNK][2];       // the layer in registers; (park_cur, park_slot) say which one and where the others are
+    int park_cur = 0, park_slot1 = 0, park_slot2 = 1, park_slot0 = 0;
+    const uint32_t t_park = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TC_TSLOTS * TC_CHUNK_N + sgrp * 20);
+#define CST(l) cst[0]
+#else
     __half2 cst[3][TC_NCHUNK][2];
+#define CST(l) cst[l]
+#endif
     uint32_t tslot = 0, tuse = 0;
     const int ts0 = 1024 + (warp ? 2048 : 0);
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)sgrp * 16;
@@ -588,7 +676,7 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
 #pragma unroll
     for (int l = 0; l < 3; ++l)
 #pragma unroll
-      for (int j = 0; j < TC_NCHUNK; ++j) cst[l][j][0] = cst[l][j][1] = __floats2half2_rn(0.f, 0.f);
+      for (int j = 0; j < TC_NCHUNK; ++j) CST(l)[j][0] = CST(l)[j][1] = __floats2half2_rn(0.f, 0.f);
     // one cell-step; the layer is a compile-time constant (the cell state of a layer lives in registers)
     auto step = [&](auto LC, const int inst, const int sidx, const int d, const int g) {
       constexpr int l = decltype(LC)::value;
@@ -625,7 +713,7 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
 #pragma unroll
       for (int l = 0; l < 3; ++l)
 #pragma unroll
-        for (int j = 0; j < TC_NCHUNK; ++j) cst[l][j][0] = cst[l][j][1] = __floats2half2_rn(0.f, 0.f);
+        for (int j = 0; j < TC_NCHUNK; ++j) CST(l)[j][0] = CST(l)[j][1] = __floats2half2_rn(0.f, 0.f);
       float cls_acc = 0.f;
       for (int d = 0; d < 13; ++d) {
 #pragma unroll
@@ -633,6 +721,30 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
           const int t = d - l;
           if (t < 0 || t > 10) continue;
           if (g >= max_steps) { ++g; continue; }
+#endif
+          if (TC_STATIC_SLOTS) tslot = 0;           // (it is 0 already: said so for constant folding in the unrolled chunks)
+#if TC_PARK
+          if (park_cur != l) {
+            // bring layer l's cell state into the registers, park the one that was there in the slot l leaves
+            const int ps = l == 0 ? park_slot0 : l == 1 ? park_slot1 : park_slot2;
+            const uint32_t pa = t_park + (uint32_t)ps * 10;
+            uint32_t* cr = reinterpret_cast<uint32_t*>(&cst[0][0][0]);
+            uint32_t nw[10];
+            if (t != 0) {                           // (at t = 0 the state of layer l is not read: c(-1) = 0)
+              tc_ld8(pa, nw);
+              tc_ld2(pa + 8, nw + 8);
+              tc_wait_ld();
+            }
+            tc_st8(pa, cr);
+            tc_st2(pa + 8, cr + 8);
+            tc_wait_st();
+            if (t != 0) {
+#pragma unroll
+              for (int i = 0; i < 10; ++i) cr[i] = nw[i];
+            }
+            if (park_cur == 0) park_slot0 = ps; else if (park_cur == 1) park_slot1 = ps; else park_slot2 = ps;
+            park_cur = l;
+          }
 #endif
           // prefetch what this step's epilogue must stage for later steps
           uint4 xnext = make_uint4(0, 0, 0, 0);
@@ -722,14 +834,25 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
             if (++tslot == TC_TSLOTS) { tslot = 0; ++tuse; }
             if (stamp) TS(ts0 + g * 16 + 3 * j + 2);
             // gate pre-activations of units (0,1) and (2,3) as f16x2 (low half = the even unit): one cvt per pair
-            // and gate, and from here on v is dead
+            // and gate, and from here on v is dead.  (TC_GATE32: the tanh of the four gates is taken in f32 from the
+            // accumulator registers and the RESULTS are packed, which saves the PRMT after every pair of MUFU.TANH.F16.)
             __half2 gi[2], gj[2], gf[2], go[2];
 #pragma unroll
             for (int p = 0; p < 2; ++p) {
-              gi[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 0]), __uint_as_float(v[8 * p + 4]));
-              gj[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 1]), __uint_as_float(v[8 * p + 5]));
-              gf[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 2]), __uint_as_float(v[8 * p + 6]));
-              go[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 3]), __uint_as_float(v[8 * p + 7]));
+              if (TC_GATE32) {
+                if (TC_FMAI) gi[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 0]), __uint_as_float(v[8 * p + 4]));
+                else gi[p] = __floats2half2_rn(tanh32_mufu(__uint_as_float(v[8 * p + 0])), tanh32_mufu(__uint_as_float(v[8 * p + 4])));
+                gj[p] = __floats2half2_rn(tanh32_mufu(__uint_as_float(v[8 * p + 1])), tanh32_mufu(__uint_as_float(v[8 * p + 5])));
+                if (TC_FMAF) gf[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 2]), __uint_as_float(v[8 * p + 6]));
+                else if (!(TC_T0SKIP && t == 0))
+                  gf[p] = __floats2half2_rn(tanh32_mufu(__uint_as_float(v[8 * p + 2])), tanh32_mufu(__uint_as_float(v[8 * p + 6])));
+                go[p] = __floats2half2_rn(tanh32_mufu(__uint_as_float(v[8 * p + 3])), tanh32_mufu(__uint_as_float(v[8 * p + 7])));
+              } else {
+                gi[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 0]), __uint_as_float(v[8 * p + 4]));
+                gj[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 1]), __uint_as_float(v[8 * p + 5]));
+                gf[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 2]), __uint_as_float(v[8 * p + 6]));
+                go[p] = __floats2half2_rn(__uint_as_float(v[8 * p + 3]), __uint_as_float(v[8 * p + 7]));
+              }
             }
             // the next chunk's accumulator load overlaps this chunk's cell update ((tslot, tuse) now name the next chunk)
             const bool nxt = TC_PREFETCH && (j + 1 < TC_NCHUNK || cross);
@@ -749,16 +872,19 @@ k_lstm_tc(const uint16_t* __restrict__ feat_tc, const int32_t* __restrict__ win_
             if (!dbg_nomath) {
 #pragma unroll
               for (int p = 0; p < 2; ++p) {
-                const __half2 ti = tanh2_mufu(gi[p]), tj = tanh2_mufu(gj[p]), to = tanh2_mufu(go[p]);
-                const __half2 y = __hmul2(__hfma2(ti, half2_half, half2_half), tj);
+                const __half2 tj = TC_GATE32 ? gj[p] : tanh2_mufu(gj[p]), to = TC_GATE32 ? go[p] : tanh2_mufu(go[p]);
+                const __half2 si = TC_FMAI ? sigmoid2_fma(gi[p])
+                                           : __hfma2(TC_GATE32 ? gi[p] : tanh2_mufu(gi[p]), half2_half, half2_half);
+                const __half2 y = __hmul2(si, tj);
                 __half2 cn;
                 if (TC_T0SKIP && t == 0) {            // c_prev == 0: the forget gate cannot matter
                   cn = y;
                 } else {
-                  const __half2 cp = cst[l][j][p];
-                  cn = __hfma2(__hfma2(cp, tanh2_mufu(gf[p]), cp), half2_half, y);
+                  const __half2 cp = CST(l)[j][p];
+                  if (TC_FMAF) cn = __hfma2(cp, sigmoid2_fma(gf[p]), y);
+                  else cn = __hfma2(__hfma2(cp, TC_GATE32 ? gf[p] : tanh2_mufu(gf[p]), cp), half2_half, y);
                 }
-                cst[l][j][p] = cn;
+                CST(l)[j][p] = cn;
                 const __half2 tc = tanh2_mufu(cn);
                 const __half2 h2 = __hfma2(tc, to, tc);
                 if (l == 2 && t == 10) {
@@ -968,7 +1094,8 @@ void dm_tc_pack_weights(const float* kernel, const float* bias, int layer, bool 
     for (int kc = 0; kc < ncols; ++kc)
       for (int n = 0; n < TC_CHUNK_N; ++n) {
         const int unit = tc_unit0(j, n / 16) + (n / 4) % 4, gate = n % 4, col = gate * DM_HIDDEN + unit;
-        const float scale = gate == 1 ? 1.0f : 0.5f;
+        // (TC_FMAF: the forget gate's pre-activation is wanted as x * log2(e), not x / 2)
+        const float scale = gate == 1 ? 1.0f : ((gate == 2 && TC_FMAF) || (gate == 0 && TC_FMAI)) ? 1.4426950408889634f : 0.5f;
         const float bsc = (bias[col] + (gate == 2 ? 1.0f : 0.0f)) * scale;
         const uint16_t bhi = h_rn16(bsc, f16), blo = h_rn16(bsc - h_rn16f(bhi, f16), f16);
         for (int e = 0; e < 8; ++e) {
