@@ -69,9 +69,12 @@ __host__ __device__ constexpr int tc_unit0(int j, int s);
 #define TC_UNIWARP 1       // warp index through a shuffle (provably warp-uniform for the compiler)
 #endif
 #ifndef TC_GATE32
-#define TC_GATE32 1        // 1: the four gate tanh are taken in f32 straight from the accumulator registers and their RESULTS
+#define TC_GATE32 0        // 1: the four gate tanh are taken in f32 straight from the accumulator registers and their RESULTS
                            //    are packed to f16x2 (8 MUFU.TANH + 4 F2FP per unit pair instead of 4 F2FP + 8 MUFU.TANH.F16 + 4 PRMT):
-                           //    same speed, the gate inputs keep their fp32 precision (mean |dp1| 1.6e-4 instead of 2.8e-4)
+                           //    the gate inputs keep their fp32 precision (mean |dp1| 1.6e-4 instead of 2.8e-4, flip rate 1.2e-4
+                           //    instead of 2.4e-4) and short kernels run at the same speed, but the build spills more (160 B) and
+                           //    draws more power: in a long run the part settles at 1695 instead of 1747 MHz under its 1000 W cap
+                           //    and delivers 96.5 instead of 99.3 Mbases/s (profiles/r02_sustained_ab.txt).  Off: throughput first.
 #endif
 #ifndef TC_FMAF
 #define TC_FMAF 0          // 1: the forget gate's sigmoid is evaluated on the FMA / ALU pipes in packed fp16 (exponent arithmetic
