@@ -131,44 +131,34 @@ def split_for_calls(batch, max_windows=MAX_WINDOWS_PER_CALL):
 
 
 class Prefetcher(object):
-    """Runs ``load(item)`` for every item on a thread, ``depth`` results ahead of the consumer (numpy releases the GIL
-    while it reads and copies, so file k+1 loads while the GPU call of file k runs).  Exceptions surface in the
-    consumer, in order."""
+    """Runs ``load(index, item)`` for the items on ``workers`` threads, at most ``ahead`` results outstanding (the one the
+    consumer holds included), and hands them out IN ORDER.  numpy and file reads release the GIL, so files k+1 and k+2
+    load while the GPU call of file k runs.  Item ``i`` may reuse whatever item ``i - ahead`` used (``index % ahead``):
+    it is only submitted once the consumer has come back for the next result.  Exceptions surface in the consumer, in order."""
 
-    def __init__(self, items, load, depth=2):
-        self._q = queue.Queue(maxsize=depth)
-        self._stop = False
-
-        def work():
-            for it in items:
-                if self._stop:
-                    break
-                try:
-                    self._q.put((it, load(it), None))
-                except BaseException as e:          # noqa: B902 - handed to the consumer
-                    self._q.put((it, None, e))
-                    break
-            self._q.put(None)
-        self._t = threading.Thread(target=work, daemon=True)
-        self._t.start()
+    def __init__(self, items, load, ahead=3, workers=2):
+        from concurrent.futures import ThreadPoolExecutor
+        self._items, self._load, self._ahead = list(items), load, max(1, ahead)
+        self._pool = ThreadPoolExecutor(max_workers=max(1, workers))
 
     def __iter__(self):
-        while True:
-            got = self._q.get()
-            if got is None:
-                return
-            item, value, err = got
-            if err is not None:
-                raise err
-            yield item, value
+        from collections import deque
+        futs, nxt = deque(), 0
+
+        def submit():
+            nonlocal nxt
+            if nxt < len(self._items):
+                futs.append((self._items[nxt], self._pool.submit(self._load, nxt, self._items[nxt])))
+                nxt += 1
+        for _ in range(self._ahead):
+            submit()
+        while futs:
+            item, f = futs.popleft()
+            yield item, f.result()
+            submit()
 
     def close(self):
-        self._stop = True
-        while self._t.is_alive():
-            try:
-                self._q.get(timeout=0.05)
-            except queue.Empty:
-                pass
+        self._pool.shutdown(wait=True, cancel_futures=True)
 
 
 def load_packed(path, contig_names, moptions, shard=None, arena=None):
@@ -201,10 +191,9 @@ def detect_handler(moptions, ctx, read_files, contig_names, failed, shard=None, 
     ``predetail.DetailWriter``) receives the per-read predictions when the per-read output is wanted (:716-782).
     Returns (reads seen, windows predicted)."""
     n_reads = n_windows = 0
-    # three page-locked arenas in rotation: one under the GPU call, one queued, one being filled (Prefetcher depth 1)
+    # three page-locked arenas in rotation: one under the GPU call, two being filled / waiting (Prefetcher ahead = 3)
     arenas = [capi.PinnedArena() for _ in range(3)]
-    order = {p: i for i, p in enumerate(read_files)}
-    pre = Prefetcher(read_files, lambda p: load_packed(p, contig_names, moptions, shard, arenas[order[p] % 3]), depth=1)
+    pre = Prefetcher(read_files, lambda i, p: load_packed(p, contig_names, moptions, shard, arenas[i % 3]), ahead=3, workers=2)
     try:
         for path, parts in pre:
             for pb, first in parts:

@@ -213,10 +213,28 @@ def test_plan_files_and_prefetcher(tmp_path):
     assert not shares[0][1] and sorted(shares[0][0] + shares[1][0]) == files and not set(shares[0][0]) & set(shares[1][0])
     load = [sum(os.path.getsize(f) for f in s[0]) for s in shares]
     assert abs(load[0] - load[1]) <= 100
-    seen = [(it, v) for it, v in detect.Prefetcher(range(5), lambda x: x * x)]
-    assert seen == [(i, i * i) for i in range(5)]
+    import threading
+    import time
+    live, peak, lock = set(), [0], threading.Lock()
 
-    def boom(x):
+    def load(i, x):                                      # slot i % 3 must be free again when item i is loaded
+        with lock:
+            assert i % 3 not in live, "slot reused while its previous item is still out"
+            live.add(i % 3)
+            peak[0] = max(peak[0], len(live))
+        time.sleep(0.01 * (3 - i % 3))                   # finish out of order
+        return x * x
+    seen = []
+    pre = detect.Prefetcher(range(100, 109), load, ahead=3, workers=2)
+    for it, v in pre:
+        seen.append((it, v))
+        time.sleep(0.005)
+        with lock:
+            live.discard((it - 100) % 3)                 # the consumer is done with it when it asks for the next one
+    pre.close()
+    assert seen == [(i, i * i) for i in range(100, 109)] and peak[0] <= 3
+
+    def boom(i, x):
         if x == 2:
             raise ValueError("bad file")
         return x
