@@ -302,7 +302,16 @@ def cli_leg(ctx, spec, local, n_files=16, reads_per_file=800):
     """files -> BED through `python -m deepmod_b200 detect` (the product's own command) on reads of the same stream
     written to disk as packed batches; the prediction phase (files -> accumulator) is what compares with `e2e`."""
     from deepmod_b200 import reads_io
+    import shutil
     d = tempfile.mkdtemp(prefix="dm_cli_")
+    try:
+        return _cli_leg(ctx, spec, local, n_files, reads_per_file, d)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
+def _cli_leg(ctx, spec, local, n_files, reads_per_file, d):
+    from deepmod_b200 import reads_io
     wrk = os.path.join(d, "reads")
     os.makedirs(wrk)
     bases = 0
@@ -330,8 +339,6 @@ def cli_leg(ctx, spec, local, n_files=16, reads_per_file=800):
                             "wall_s = the whole process incl. python start-up")
     if r.returncode != 0:
         out["stderr"] = r.stderr[-400:]
-    import shutil
-    shutil.rmtree(d, ignore_errors=True)
     return out
 
 

@@ -70,3 +70,65 @@ def test_bad_alignment_status(golden_batch):
         ctx.set_genome(lens, "C")
         _, pred, status = ctx.detect_batch(bad)
         assert status[4] == capi.READ_BAD_ALIGN and status[5] == capi.READ_OK
+
+
+def test_round2_entry_points_edge_cases(golden_batch):
+    """Empty inputs and bad arguments of the entry points added in round 2: reduce / merge / totals, stored records,
+    the device-side generator, pinned staging."""
+    from deepmod_b200 import capi, checkpoint
+    batch, names, lens = golden_batch
+    model = checkpoint.Model.from_dict(golden_model("conmodC_P100"))
+    with capi.Context(model, 0) as ctx, capi.Context(model, 0) as other:
+        spec = ctx.synth_spec(seed=1)
+        with pytest.raises(capi.DeepModError, match="dm_set_genome not called"):
+            ctx.synth_generate(spec, 0, 4)
+        with pytest.raises(capi.DeepModError, match="dm_set_genome not called"):
+            ctx.hist_totals()
+        with pytest.raises(capi.DeepModError, match="dm_set_genome not called"):
+            ctx.reduce_comm(None, 0, 2)
+        ctx.set_genome(lens, "C")
+        assert ctx.hist_totals() == (0, 0, 0, 0)
+        assert ctx.reduce_comm(None, 0, 1) == 0.0                       # one rank: nothing to exchange, no NCCL needed
+        ctx.reduce_finalize()                                           # and nothing to tear down
+        capi.reduce_contexts([ctx])
+        with pytest.raises(capi.DeepModError):
+            ctx.reduce_comm(None, 3, 2)                                 # rank outside the world
+        with pytest.raises(capi.DeepModError, match="an id is required"):
+            ctx.reduce_comm(None, 0, 2)
+        with pytest.raises(capi.DeepModError, match="two contexts on one device"):
+            other.set_genome(lens, "C")
+            capi.reduce_contexts([ctx, other])
+        other.set_genome(lens[:1], "C")
+        with pytest.raises(capi.DeepModError, match="different genomes"):
+            ctx.hist_merge(other)
+        # generator: empty range, bad spec
+        assert ctx.synth_generate(spec, 5, 0) == 0 and ctx.resident_sizes() == (0, 0, 0, 0)
+        ctx.detect_resident(True)                                       # an empty resident batch is a no-op
+        ev, win = ctx.synth_describe(spec, 0, 0)
+        assert len(ev) == 0 and len(win) == 0
+        with pytest.raises(capi.DeepModError, match="max_clip"):
+            ctx.synth_generate(ctx.synth_spec(seed=1, len_lo=40, len_hi=50, max_clip=30), 0, 2)
+        # a read longer than its contig is cut to the contig
+        ctx.set_genome([700], "C")
+        nw = ctx.synth_generate(ctx.synth_spec(seed=3, mean_len=8000.0, len_lo=600, len_hi=60000, max_clip=10), 0, 5)
+        b = ctx.fetch_inputs()
+        assert nw > 0 and b["col_refpos"].max() < 700 and b["col_refpos"].min() >= 0
+        # stored records: empty call, unknown contig
+        ctx.accumulate_records(0, "+", np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int8))
+        with pytest.raises(capi.DeepModError, match="contig out of range"):
+            ctx.accumulate_records(4, "+", np.zeros(1, np.uint8), np.zeros(1, np.uint8), np.zeros(1, np.int64), np.zeros(1, np.int8))
+        # records outside the contig are ignored like reads are; a deletion creates the row without coverage
+        ctx.hist_clear()
+        ctx.accumulate_records(0, "-", np.frombuffer(b"CCCA", np.uint8), np.frombuffer(b"C-CA", np.uint8),
+                               np.array([5, 6, 9999, 7], np.int64), np.array([1, 0, 1, 1], np.int8))
+        pos, cov, mod = ctx.hist_nonzero(0, "-")
+        assert list(pos) == [5, 6] and list(cov) == [1, 0] and list(mod) == [1, 0]
+    arena = capi.PinnedArena(1 << 20)
+    a = arena.alloc((1000,), np.float32)
+    a[:] = 3.0
+    big = arena.alloc((1 << 20,), np.int64)                             # does not fit: pageable fallback, still usable
+    big[-1] = 7
+    assert a.sum() == 3000.0 and big[-1] == 7 and len(arena.overflow) == 1
+    arena.reset(64 << 20)                                               # grows
+    assert arena.size >= 64 << 20 and arena.alloc((8,), np.uint8).nbytes == 8
+    arena.close()
