@@ -171,28 +171,30 @@ def read_file_list(cur_cif, cur_strand):
     return out, base_out
 
 
-class _DetailCache(object):
-    """Open detail containers (one batch file holds many reads)."""
+class _Detail(object):
+    """One detail file: ``get(key) -> (refbase, readbase, refbasei, mod_pred, chr, strand)``; ``contig_len(keys)``."""
 
-    def __init__(self):
-        self.path, self.z, self.index = None, None, None
+    def __init__(self, path):
+        self.path, self.z = path, None
+        if zipfile.is_zipfile(path):
+            with np.load(path, allow_pickle=False) as f:
+                self.z = {k: f[k] for k in f.files}
+            self.index = {str(k): i for i, k in enumerate(self.z["keys"])}
 
-    def get(self, path, key):
-        if path != self.path:
-            self.path = path
-            if zipfile.is_zipfile(path):
-                with np.load(path, allow_pickle=False) as z:
-                    self.z = {k: z[k] for k in z.files}
-                self.index = {str(k): i for i, k in enumerate(self.z["keys"])}
-            else:
-                self.z, self.index = None, None
+    def get(self, key):
+        if self.z is None:
+            return read_detail_hdf5(self.path, key)[:6]          # a file the reference wrote
+        z, i = self.z, self.index[key]
+        a, b = int(z["rec_off"][i]), int(z["rec_off"][i + 1])
+        return (z["refbase"][a:b], z["readbase"][a:b], z["refbasei"][a:b].astype(np.int64), z["mod_pred"][a:b].astype(np.int8),
+                str(z["mapped_chr"][i]), str(z["mapped_strand"][i]))
+
+    def contig_len(self, keys):
+        """Length of the contig these reads map to: stored in the container; for the reference's files (which do not
+        record it) the largest stored position + 1."""
         if self.z is not None:
-            i = self.index[key]
-            a, b = int(self.z["rec_off"][i]), int(self.z["rec_off"][i + 1])
-            z = self.z
-            return (z["refbase"][a:b], z["readbase"][a:b], z["refbasei"][a:b].astype(np.int64), z["mod_pred"][a:b].astype(np.int8),
-                    str(z["mapped_chr"][i]), str(z["mapped_strand"][i]), int(z["contig_len"][i]))
-        return read_detail_hdf5(path, key)
+            return max([int(self.z["contig_len"][self.index[k]]) for k in keys] + [0])
+        return max([int(self.get(k)[2].max()) + 1 for k in keys] + [0])
 
 
 def read_detail_hdf5(path, key):
@@ -268,24 +270,35 @@ def summarise_stored(moptions):
         raise capi.DeepModError("no %s.<chr> index files under %s" % (PRE_BASE_STR, predpath))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     written = []
-    cache = _DetailCache()
     with capi.Context(checkpoint.random_model(0), device=local) as ctx:                   # the model is not used in this phase
         for cif in ind_files:
             chrom = cif.split(PRE_BASE_STR)[-1][1:]                                         # :1242
             entries = {s: read_file_list(cif, s) for s in "+-"}
             base_out = entries["+"][1] or entries["-"][1] or (predpath + "/")
-            clen = 0
-            for s in "+-":                       # contig length: from the container, else the largest stored position
-                for lsp in entries[s][0]:
-                    rec = cache.get(base_out + "/" + lsp[5], lsp[3])
-                    clen = max(clen, rec[6], int(rec[2].max()) + 1 if len(rec[2]) else 0)
-            ctx.set_genome([clen], moptions["Base"])
+            # the sum does not depend on the order: group the reads by detail file, open every file once
+            by_file = defaultdict(list)
             for s in "+-":
                 for lsp in entries[s][0]:
-                    rb, qb, rp, mp, mchr, mstrand, _ = cache.get(base_out + "/" + lsp[5], lsp[3])
-                    if not (mchr == chrom and mstrand == s):                                # :1055-1056
-                        print("ERRoR not the same chr (real=%s vs expect=%s) and strand (real=%s VS expect=%s)" % (mchr, chrom, mstrand, s))
-                    ctx.accumulate_records(0, s, rb, qb, rp, mp)
+                    by_file[base_out + "/" + lsp[5]].append((s, lsp[3]))
+            clen = 0
+            for path in sorted(by_file):
+                clen = max(clen, _Detail(path).contig_len([key for _, key in by_file[path]]))
+            ctx.set_genome([clen], moptions["Base"])
+            for path in sorted(by_file):                   # one file in memory at a time, one accumulate call per strand
+                det = _Detail(path)
+                for s in "+-":
+                    recs = []
+                    for st, key in by_file[path]:
+                        if st != s:
+                            continue
+                        rec = det.get(key)
+                        if not (rec[4] == chrom and rec[5] == s):                            # :1055-1056
+                            print("ERRoR not the same chr (real=%s vs expect=%s) and strand (real=%s VS expect=%s)" % (rec[4], chrom, rec[5], s))
+                        recs.append(rec)
+                    if recs:
+                        ctx.accumulate_records(0, s, np.concatenate([r[0] for r in recs]), np.concatenate([r[1] for r in recs]),
+                                               np.concatenate([r[2] for r in recs]), np.concatenate([r[3] for r in recs]))
+            for s in "+-":
                 path = "%s/mod_pos.%s%s.%s.bed" % (out_dir, chrom, s, moptions["Base"])   # :1043
                 if ctx.write_bed(0, s, chrom, path) > 0:
                     written.append(path)
