@@ -4,7 +4,9 @@
 
 mirrors ``python hm_cluster_predict.py <prefix> <motif folder>`` (``:76-78``): for every chromosome it reads
 ``<prefix>.<chr>.C.bed`` and ``<motif folder>/motif_<chr>_C.bed`` and writes ``<prefix>_clusterCpG.<chr>.C.bed``.
-Inside ``detect`` the same kernels run straight on the GPU accumulator (no BED round trip).
+The same kernels also run straight on a GPU accumulator, without the BED round trip (``dm_cluster_set_sites`` /
+``dm_cluster_predict`` after ``dm_detect_*`` and ``dm_reduce*``: the ``hg38_scale`` leg of ``bench.py`` does that on the
+reduced 49 GB accumulator); ``detect`` itself never calls them, exactly like the reference's ``detect``.
 """
 import argparse
 import os
