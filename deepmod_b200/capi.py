@@ -102,7 +102,7 @@ SIGNATURES = {
     "dm_batch_upload": (C.c_int, [C.c_void_p, C.POINTER(DmBatch), _i64p]),
     "dm_detect_resident": (C.c_int, [C.c_void_p, C.c_int]),
     "dm_set_pipeline": (C.c_int, [C.c_void_p, C.c_int]),
-    "dm_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "dm_pinned_alloc": (C.c_int, [C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "dm_pinned_free": (None, [C.c_void_p]),
     "dm_fetch_results": (C.c_int, [C.c_void_p, _fp, _u8p, _i32p]),
     "dm_build_windows": (C.c_int, [C.c_void_p, _fp]),
@@ -195,8 +195,9 @@ class PinnedArena(object):
     whole buffer available again.  Grows (re-allocates) when a request does not fit -- never while arrays of the
     current round are alive, because a round starts with ``reset(need)``."""
 
-    def __init__(self, nbytes=0):
+    def __init__(self, nbytes=0, device=-1):
         self.lib = load_library()
+        self.device = int(device)
         self.ptr, self.size, self.used = C.c_void_p(), 0, 0
         self.overflow = []                      # pageable arrays handed out when the buffer was too small
         if nbytes:
@@ -205,7 +206,7 @@ class PinnedArena(object):
     def _grow(self, nbytes):
         self.close()
         p = C.c_void_p()
-        rc = self.lib.dm_pinned_alloc(int(nbytes), C.byref(p))
+        rc = self.lib.dm_pinned_alloc(int(nbytes), self.device, C.byref(p))
         if rc != 0:
             msg = self.lib.dm_last_error(None)
             raise DeepModError("dm_pinned_alloc failed (%d): %s" % (rc, msg.decode() if msg else "?"))

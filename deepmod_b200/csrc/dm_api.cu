@@ -534,10 +534,12 @@ extern "C" {
 
 // page-locked host memory for callers that stage their input files themselves (a loader thread reading
 // file k+1 into one of these while dm_detect_batch works on file k): copies from it are truly asynchronous
-int dm_pinned_alloc(size_t bytes, void** out) {
+int dm_pinned_alloc(size_t bytes, int device, void** out) {
   if (!out) return DM_ERR_ARG;
   *out = nullptr;
-  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  // (the allocating thread needs a current device: name it, or a loader thread would open a context on device 0)
+  cudaError_t e = device >= 0 ? cudaSetDevice(device) : cudaSuccess;
+  if (e == cudaSuccess) e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
   if (e != cudaSuccess) { dm_set_error(nullptr, std::string("dm_pinned_alloc: ") + cudaGetErrorString(e)); return DM_ERR_CUDA; }
   return DM_OK;
 }

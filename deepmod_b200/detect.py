@@ -184,16 +184,23 @@ def load_packed(path, contig_names, moptions, shard=None, arena=None):
     return out
 
 
-def detect_handler(moptions, ctx, read_files, contig_names, failed, shard=None, detail=None):
+def start_prefetch(read_files, contig_names, moptions, shard=None, device=0):
+    """Loader threads for the packed files of this rank: three page-locked arenas in rotation (one under the GPU call,
+    two being filled / waiting).  (Starting them before the GPU context exists was measured and is not faster: the
+    arenas' cudaHostAlloc calls then queue behind the context creation.)  -> (prefetcher, arenas)"""
+    arenas = [capi.PinnedArena(device=device) for _ in range(3)]
+    pre = Prefetcher(read_files, lambda i, p: load_packed(p, contig_names, moptions, shard, arenas[i % 3]), ahead=3, workers=2)
+    return pre, arenas
+
+
+def detect_handler(moptions, ctx, read_files, contig_names, failed, shard=None, detail=None, prefetch=None):
     """Per-GPU worker: run every packed batch assigned to this rank through the C ABI.
 
     ``failed`` collects ``{reason: [read ids]}`` like ``sp_options["Error"]`` (:54-57); ``detail`` (a
     ``predetail.DetailWriter``) receives the per-read predictions when the per-read output is wanted (:716-782).
     Returns (reads seen, windows predicted)."""
     n_reads = n_windows = 0
-    # three page-locked arenas in rotation: one under the GPU call, two being filled / waiting (Prefetcher ahead = 3)
-    arenas = [capi.PinnedArena() for _ in range(3)]
-    pre = Prefetcher(read_files, lambda i, p: load_packed(p, contig_names, moptions, shard, arenas[i % 3]), ahead=3, workers=2)
+    pre, arenas = prefetch if prefetch is not None else start_prefetch(read_files, contig_names, moptions, shard, ctx.device)
     try:
         for path, parts in pre:
             for pb, first in parts:
@@ -381,6 +388,7 @@ def mDetect_manager(moptions):
     error = None
     written = []
     timing = {}
+    prefetch = None
     with capi.Context(model, device=local, precision=PRECISIONS[prec_name]) as ctx:
         detail = None
         try:
@@ -392,7 +400,8 @@ def mDetect_manager(moptions):
                 detail = predetail.DetailWriter(out_dir, moptions["wrkBase"], rank, contig_len)
             if my_reads:
                 n_reads, n_windows = detect_handler(moptions, ctx, my_reads, contig_names, failed,
-                                                    (rank, world) if shard_reads else None, detail)
+                                                    (rank, world) if shard_reads else None, detail, prefetch)
+                prefetch = None
             if my_sams:
                 for ci, seq in enumerate(ref_seqs):
                     ctx.set_contig_sequence(ci, seq)
@@ -403,6 +412,10 @@ def mDetect_manager(moptions):
                 detail.close()
         except Exception as e:                      # every rank must reach the exchange below, or the others hang in it
             error = "%s: %s" % (type(e).__name__, e)
+        if prefetch is not None:                    # an error before the files were consumed: stop the loader threads
+            prefetch[0].close()
+            for a in prefetch[1]:
+                a.close()
         timing["predict_s"] = time.time() - (t_pred if "init_s" in timing else start_time)
         # one small object per rank: failure, rejected reads, counts (rank 0 used to report only its own)
         reports = ranks.gather((error, failed, n_reads, n_windows))

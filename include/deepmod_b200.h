@@ -199,7 +199,7 @@ int dm_detect_batch(dm_ctx* ctx, const dm_batch* b, float* p1_out, uint8_t* pred
                     int32_t* status_out);
 /* Page-locked host memory for input staging (optional: dm_detect_batch takes any host pointer; from these buffers its
  * copies overlap the kernels without a driver-side staging pass). */
-int  dm_pinned_alloc(size_t bytes, void** out);
+int  dm_pinned_alloc(size_t bytes, int device /* the GPU the calling thread will feed; < 0: its current device */, void** out);
 void dm_pinned_free(void* p);
 /* dm_detect_batch cuts a large batch into contiguous read ranges and alternates them between two
  * device slots / streams, so the host<->device copies of one range run under the kernels of the
