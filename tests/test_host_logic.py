@@ -241,3 +241,37 @@ def test_plan_files_and_prefetcher(tmp_path):
     with pytest.raises(ValueError, match="bad file"):
         for _ in detect.Prefetcher(range(5), boom):
             pass
+
+
+def test_stored_npz_reader_equals_numpy_and_falls_back(batch, tmp_path):
+    """reads_io reads the members of an uncompressed .npz straight from their byte ranges (no zipfile CRC pass);
+    anything else goes through numpy's own reader."""
+    b, _ = batch
+    p = str(tmp_path / "a.dmreads.npz")
+    reads_io.save_reads(p, dict(b, aln_pos=np.arange(len(b["start_clip"]), dtype=np.int64)), ["c1", "chr_2"], [50000, 20000])
+    got, names, lens = reads_io.load_reads(p)
+    assert names == ["c1", "chr_2"] and list(lens) == [50000, 20000]
+    with np.load(p) as z:
+        assert sorted(got) == sorted(k for k in z.files if k not in ("contig_names", "contig_len"))
+        for k in got:
+            assert got[k].dtype == z[k].dtype and np.array_equal(got[k], z[k]), k
+    assert reads_io.load_reads(p, header_only=True)[0] is None
+    handed = []
+
+    def alloc(shape, dtype):                               # caller-supplied memory (the loader's page-locked arenas)
+        a = np.zeros(shape, dtype)
+        handed.append(a)
+        return a
+    got2, _, _ = reads_io.load_reads(p, alloc=alloc)
+    assert any(got2["ev_mean"] is a for a in handed) and np.array_equal(got2["ev_mean"], got["ev_mean"])
+    c = str(tmp_path / "c.dmreads.npz")                    # compressed members: numpy's reader
+    np.savez_compressed(c, contig_names=np.array(["c1", "chr_2"]), contig_len=np.array([50000, 20000]), **b)
+    assert reads_io._read_stored_npz(c, None) is None
+    got3, names3, _ = reads_io.load_reads(c)
+    assert names3 == names and np.array_equal(got3["col_refpos"], b["col_refpos"])
+    raw = open(p, "rb").read()                             # a truncated member is an error, not silent garbage
+    t = str(tmp_path / "t.dmreads.npz")
+    with open(t, "wb") as fh:
+        fh.write(raw[:len(raw) // 3])
+    with pytest.raises(Exception):
+        reads_io.load_reads(t)
