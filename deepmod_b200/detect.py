@@ -374,7 +374,17 @@ def mDetect_manager(moptions):
         os.makedirs(out_dir, exist_ok=True)                                         # :1151-1152
 
     ranks = _Ranks(world, rank)
-    uid = ranks.broadcast(capi.reduce_unique_id() if (world > 1 and rank == 0) else None)
+    uid = None
+    if world > 1:                                   # rank 0 makes the NCCL id; a failure there reaches every rank too
+        if rank == 0:
+            try:
+                uid = capi.reduce_unique_id()
+            except capi.DeepModError as e:
+                uid = e
+        uid = ranks.broadcast(uid)
+        if isinstance(uid, Exception):
+            ranks.close()
+            raise capi.DeepModError("multi-GPU detect needs NCCL: %s" % uid)
     ref_seqs = None
     if sam_files:
         contig_names, ref_seqs = reads_io.read_fasta(moptions["Ref"])
@@ -389,9 +399,12 @@ def mDetect_manager(moptions):
     written = []
     timing = {}
     prefetch = None
-    with capi.Context(model, device=local, precision=PRECISIONS[prec_name]) as ctx:
-        detail = None
+    ctx = None
+    detail = None
+    try:
         try:
+            # (inside the try: a rank whose context cannot be created must still reach the gather below)
+            ctx = capi.Context(model, device=local, precision=PRECISIONS[prec_name])
             ctx.set_genome(contig_len, moptions["Base"])
             timing["init_s"] = time.time() - start_time          # file discovery, model load, CUDA context, accumulator
             t_pred = time.time()
@@ -421,7 +434,6 @@ def mDetect_manager(moptions):
         reports = ranks.gather((error, failed, n_reads, n_windows))
         errors = ["rank %d: %s" % (i, r[0]) for i, r in enumerate(reports) if r[0]]
         if errors:
-            ranks.close()
             raise capi.DeepModError("detect failed on %d of %d ranks: %s" % (len(errors), world, "; ".join(errors)))
         failed = {}
         for r in reports:
@@ -451,6 +463,9 @@ def mDetect_manager(moptions):
                     n_reads, n_windows, n_windows / max(timing["predict_s"], 1e-9), len(written), timing))
             with open(out_dir + ".done", "a"):                                      # :1263
                 os.utime(out_dir + ".done", None)
-    ranks.close()
+    finally:
+        if ctx is not None:
+            ctx.close()
+        ranks.close()
     sys.stdout.flush()
     return {"reads": n_reads, "bases": n_windows, "beds": written, "failed": failed, "timing": timing}

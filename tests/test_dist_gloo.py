@@ -68,3 +68,33 @@ def test_two_rank_reduce_equals_single_process(tmp_path):
     got = ocells.acc_from_cells(merged, ["c1", "c2"], [20000, 12000], "C")
     assert got == acc
     assert detect_ref.bed_by_contig_strand(got) == detect_ref.bed_by_contig_strand(acc)
+
+
+def test_a_failing_rank_fails_every_rank_instead_of_hanging(tmp_path, golden_batch):
+    """The product's own manager at world size 2 (gloo control plane): a rank that cannot do its work -- here: no GPU
+    in this container, so dm_create fails on both -- is gathered and raised on EVERY rank before the exchange step; the
+    job ends promptly with a non-zero exit code instead of leaving ranks in a collective."""
+    import subprocess
+    import sys
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: the ranks would succeed")
+    except ImportError:
+        pytest.skip("torch is not installed")
+    from conftest import ROOT, golden_model
+    from deepmod_b200 import checkpoint, reads_io
+    batch, names, lens = golden_batch
+    wrk = tmp_path / "reads"
+    wrk.mkdir()
+    for i in range(3):
+        reads_io.save_reads(str(wrk / ("p%d.dmreads.npz" % i)), batch, names, lens)
+    mod = str(tmp_path / "m.npz")
+    checkpoint.save_npz(checkpoint.Model.from_dict(golden_model("conmodC_P100")), mod)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29655", "-m", "deepmod_b200", "detect", "--wrkBase", str(wrk), "--modfile", mod,
+                        "--Base", "C", "--FileID", "x", "--outFolder", str(tmp_path / "out")],
+                       capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert r.returncode != 0
+    assert "detect failed on 2 of 2 ranks" in r.stderr and "no CPU path" in r.stderr
+    assert not (tmp_path / "out" / "x.done").exists()
