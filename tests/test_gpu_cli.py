@@ -73,3 +73,39 @@ def test_detect_two_ranks_nccl_equals_single(tmp_path, golden_batch):
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert _beds(os.path.join(out, "r3"), golden_batch[1], g["base"]) == g["bed"]
+
+
+def test_detect_two_ranks_files_dealt_out(tmp_path, golden_batch):
+    """More files than ranks: the FILES are dealt out (no rank reads another rank's input), the accumulators are summed
+    inside the library (dm_reduce_comm) and the BED files equal the single-GPU reference output."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from deepmod_b200 import checkpoint, reads_io, synth
+    tag = "conmodC_P100"
+    g = golden_reads(tag)
+    batch, names, lens = golden_batch
+    wrk = tmp_path / "reads"
+    wrk.mkdir()
+    n = len(batch["start_clip"])
+    for i, (lo, hi) in enumerate(((0, 3), (3, 4), (4, n))):                  # three files of different sizes
+        reads_io.save_reads(str(wrk / ("part%d.dmreads.npz" % i)), synth.slice_reads(batch, lo, hi), names, lens)
+    mod = str(tmp_path / "m.npz")
+    checkpoint.save_npz(checkpoint.Model.from_dict(golden_model(tag)), mod)
+    out = str(tmp_path / "out")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29633", "-m", "deepmod_b200", "detect",
+                        "--wrkBase", str(wrk), "--modfile", mod, "--Base", g["base"], "--FileID", "r4", "--outFolder", out,
+                        "--saveDetail", "1"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert _beds(os.path.join(out, "r4"), names, g["base"]) == g["bed"]
+    # rejected reads of BOTH ranks are reported (rank 0 used to print only its own)
+    assert "Error Does not match 1" in r.stdout.replace("\t", " ") and "Less Event 1" in r.stdout.replace("\t", " ")
+    # per-rank detail folders + merged index files, and the stored predictions reproduce the BED files
+    assert os.path.isdir(os.path.join(out, "r4", "0")) and os.path.isdir(os.path.join(out, "r4", "1"))
+    out2 = str(tmp_path / "out2")
+    r2 = subprocess.run([sys.executable, "-m", "deepmod_b200", "detect", "--wrkBase", str(wrk), "--predDet", "0", "--predpath",
+                         os.path.join(out, "r4"), "--Base", g["base"], "--FileID", "r5", "--outFolder", out2],
+                        capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+    assert _beds(os.path.join(out2, "r5"), names, g["base"]) == g["bed"]
