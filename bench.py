@@ -653,7 +653,7 @@ def main():
         line["hg38_scale"] = hg38
 
     # ---- the three arithmetics on ONE >= 1 M-window subsample of the stream: throughput, flip rate, BED rows ----
-    if not args.no_parity_leg:
+    def parity_leg():
         _, win = ctx.synth_describe(spec, 0, R)
         n_sub = int(min(R, np.searchsorted(np.cumsum(win), 1200000) + 1))
         res = {}
@@ -680,7 +680,18 @@ def main():
                            "pred_flip_rate_vs_fp32": float(np.mean(r_[1] != ref[1])), "max_abs_dp1": float(d.max()),
                            "mean_abs_dp1": float(d.mean()), "bed_rows_mod_changed": changed, "bed_rows_pct_changed": changed_pct,
                            "bed_rows_changed_frac": changed / max(rows, 1)}
-        line["other_precision"] = arith
+        return arith
+
+    if not args.no_parity_leg:
+        try:
+            line["other_precision"] = parity_leg()
+        except Exception as e:                      # never lose the headline line over an auxiliary leg
+            line["other_precision"] = {"error": "%s: %s" % (type(e).__name__, e)}
+            try:
+                ctx.set_precision(prec)
+                ctx.hist_clear()
+            except Exception:
+                pass
 
     # ---- the widened rows (configs[3]; files -> BED): short legs ----
     if world == 1 and not args.no_next_rows:
@@ -697,14 +708,18 @@ def main():
 
     # ---- CPU baseline on the host cores (bounded sample, the reference's process model) ----
     if world == 1 and not args.no_cpu_baseline:
-        procs = os.cpu_count() or 1
-        pool = CpuPool(weights, procs)
-        shards, _ = cpu_sample(procs, 4)            # ~10-20 s of CPU work on the GPU box's host cores
-        n_cpu, secs = pool.run(shards)
-        pool.close()
-        line["cpu_baseline"] = {"value": n_cpu / secs / 1e6, "unit": UNIT, "cores": procs, "kind": "port",
-                                "sample": "%d reads of the same distribution (%d bases), 4 per single-threaded worker process, "
-                                          "one pass, %.1f s" % (4 * procs, n_cpu, secs)}
+        try:
+            procs = os.cpu_count() or 1
+            pool = CpuPool(weights, procs)
+            shards, _ = cpu_sample(procs, 4)            # ~10-20 s of CPU work on the GPU box's host cores
+            n_cpu, secs = pool.run(shards)
+            pool.close()
+            line["cpu_baseline"] = {"value": n_cpu / secs / 1e6, "unit": UNIT, "cores": procs, "kind": "port",
+                                    "sample": "%d reads of the same distribution (%d bases), 4 per single-threaded worker process, "
+                                              "one pass, %.1f s" % (4 * procs, n_cpu, secs)}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": "failed: %s: %s" % (type(e).__name__, e)}
     print(json.dumps(line))
     sys.stdout.flush()
     ctx.close()
