@@ -52,3 +52,23 @@ def test_product_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_header_is_plain_c_and_a_c_client_links(tmp_path):
+    """include/deepmod_b200.h compiles as C99 with -Wall -Werror, and a C program linked against the library gets status
+    codes through the boundary (examples/c_abi_probe.c).  Without a GPU its dm_create fails with DM_ERR_CUDA: exit 0."""
+    import shutil
+    import subprocess
+    from deepmod_b200 import build, capi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    build.build()
+    exe = str(tmp_path / "probe")
+    lib_dir = os.path.dirname(capi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_abi_probe.c"), "-L", lib_dir, "-ldeepmod_b200", "-Wl,-rpath," + lib_dir,
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "dm_version" in r.stdout
