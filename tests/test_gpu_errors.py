@@ -132,3 +132,23 @@ def test_round2_entry_points_edge_cases(golden_batch):
     arena.reset(64 << 20)                                               # grows
     assert arena.size >= 64 << 20 and arena.alloc((8,), np.uint8).nbytes == 8
     arena.close()
+
+
+def test_c_client_runs_the_call_sequence(tmp_path):
+    """examples/c_abi_probe.c on a GPU box: create, set_genome, an empty detect call, the 1-rank exchange, totals."""
+    import os
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    from deepmod_b200 import capi
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "probe")
+    lib_dir = os.path.dirname(capi.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_abi_probe.c"), "-L", lib_dir, "-ldeepmod_b200", "-Wl,-rpath," + lib_dir,
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "status 0, rows 0, totals 0 0 0 0" in r.stdout
