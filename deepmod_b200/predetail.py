@@ -305,3 +305,30 @@ def summarise_stored(moptions):
     with open(out_dir + ".done", "a"):
         os.utime(out_dir + ".done", None)
     return {"beds": written}
+
+
+def convert_run(run_dir):
+    """``<outFolder><FileID>`` written with ``--saveDetail 1`` -> the reference's on-disk names: every
+    ``<ct>/rnn.pred.detail.dmpd.<batch>`` becomes ``<ct>/rnn.pred.detail.fast5.<batch>`` (HDF5, needs h5py) and the index
+    files (per batch and merged) point at the new names.  -> list of HDF5 files written."""
+    written = []
+    for path in sorted(glob.glob(os.path.join(run_dir, "*", DETAIL_NAME + ".*"))):
+        out = path.replace(DETAIL_NAME + ".", "rnn.pred.detail.fast5.")
+        to_hdf5(path, out)
+        written.append(out)
+    for ind in glob.glob(os.path.join(run_dir, "*", "*." + PRE_BASE_STR + ".*")) + glob.glob(os.path.join(run_dir, PRE_BASE_STR + ".*")):
+        with open(ind) as fh:
+            text = fh.read()
+        with open(ind, "w") as fh:
+            fh.write(text.replace("/" + DETAIL_NAME + ".", "/rnn.pred.detail.fast5."))
+    return written
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) == 3 and sys.argv[1] == "to-hdf5":
+        for p in convert_run(sys.argv[2]):
+            print(p)
+    else:
+        print("usage: python -m deepmod_b200.predetail to-hdf5 <outFolder><FileID>")
+        sys.exit(2)

@@ -141,3 +141,117 @@ def test_saved_detail_resumes_to_the_same_bed(tmp_path):
     for p in res["beds"]:
         q = os.path.join(out2, "resumed", os.path.basename(p))
         assert open(p).read() == open(q).read(), os.path.basename(p)
+
+
+class _FakeDataset(object):
+    def __init__(self, data):
+        self._d = np.array(data)
+        self.value = self._d                      # the h5py 2.x attribute read_pred_detail uses (myDetect.py:1020)
+
+    def __getitem__(self, k):
+        return self._d[k]
+
+
+class _FakeGroup(dict):
+    """The part of h5py's object model the reference's writer (:722-753) and reader (:1015-1026) use."""
+
+    def __init__(self):
+        super().__init__()
+        self.attrs = {}
+
+    def _walk(self, path):
+        node = self
+        for part in [p for p in path.split("/") if p]:
+            node = dict.__getitem__(node, part)
+        return node
+
+    def __getitem__(self, path):
+        return self._walk(path)
+
+    def __contains__(self, name):
+        return dict.__contains__(self, name)
+
+    def create_group(self, name):
+        g = _FakeGroup()
+        dict.__setitem__(self, name, g)
+        return g
+
+    def require_group(self, name):
+        return dict.__getitem__(self, name) if dict.__contains__(self, name) else self.create_group(name)
+
+    def create_dataset(self, name, data=None, compression=None):
+        assert compression == "gzip"              # what the reference asks for (:753)
+        dict.__setitem__(self, name, _FakeDataset(data))
+
+
+class _FakeFile(_FakeGroup):
+    store = {}
+
+    def __init__(self, path, mode="r"):
+        super().__init__()
+        self.path = path
+        if path in _FakeFile.store:
+            old = _FakeFile.store[path]
+            self.update(old)
+            self.attrs = old.attrs
+        _FakeFile.store[path] = self
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted")
+def test_converted_detail_is_read_by_the_unmodified_read_pred_detail(packed, tmp_path, monkeypatch):
+    """predetail.to_hdf5 writes the reference's layout -- /pred/<key>/predetail + the group attributes (:722-753) -- and
+    the reference's OWN reader (read_pred_detail, :1015-1026) gets our records back from it.  No HDF5 library exists in
+    this image, so the file object is an in-memory stand-in for h5py's object model: this pins group names, dataset
+    name, attribute names and the compound dtype, not the bytes on disk."""
+    import sys
+    import types
+    batch, pb, pred, status = packed
+    names = ["chrA", "chrB"]
+    out_dir = str(tmp_path / "o" / "mod")
+    wrk = str(tmp_path / "in")
+    os.makedirs(wrk)
+    w = predetail.DetailWriter(out_dir, wrk, rank=0, contig_len=[30000, 12000])
+    container = w.add_batch(os.path.join(wrk, "b.dmreads.npz"), np.arange(pb.n_reads), pb, pred, status, names)
+    md = ref_harness.import_myDetect()
+    fake = types.ModuleType("h5py")
+    fake.File = _FakeFile
+    _FakeFile.store = {}
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    monkeypatch.setattr(md, "h5py", fake, raising=False)
+    if not hasattr(np, "int"):
+        monkeypatch.setattr(np, "int", int, raising=False)                 # removed in numpy 1.24 (myDetect.py:1022)
+    h5_rel = "0/rnn.pred.detail.fast5.0"
+    predetail.to_hdf5(container, os.path.join(out_dir, h5_rel))
+    recs = predetail.records_of(container)
+    assert len(recs) == int((status == capi.READ_OK).sum())
+    sp_options = {"base_folder_output": out_dir}
+    for key, (attrs, rec) in recs.items():
+        f5info = [attrs["mapped_chr"], attrs["mapped_strand"], str(attrs["mapped_start"]), key, attrs["f5file"], h5_rel]
+        m_pred, chrom, strand = md.read_pred_detail({}, sp_options, f5info)   # the reference's reader
+        assert (chrom, strand) == (attrs["mapped_chr"], attrs["mapped_strand"])
+        assert m_pred.dtype.names == ("refbase", "readbase", "refbasei", "readbasei", "mod_pred")
+        assert list(m_pred["refbase"]) == [x.decode() for x in rec["refbase"]]
+        assert list(m_pred["readbase"]) == [x.decode() for x in rec["readbase"]]
+        assert np.array_equal(m_pred["refbasei"], rec["refbasei"]) and np.array_equal(m_pred["mod_pred"], rec["mod_pred"])
+        grp = _FakeFile.store[os.path.join(out_dir, h5_rel)]["/pred/%s" % key]
+        for a in ("mapped_start", "mapped_end", "clipped_bases_start", "clipped_bases_end", "num_insertions", "num_deletions",
+                  "num_matches", "num_mismatches", "pred_mod_num", "f5file", "readk"):          # :727-748
+            assert a in grp.attrs
+    # the whole-run converter: reference file names, index files re-pointed
+    _FakeFile.store = {}
+    predetail.merge_index_files(out_dir, wrk)
+    done = predetail.convert_run(out_dir)
+    assert [os.path.relpath(x, out_dir) for x in done] == [h5_rel]
+    for ind in ("0/chrA.rnn.pred.ind.0", "rnn.pred.ind.chrA"):
+        lines = [l for l in open(os.path.join(out_dir, ind)).read().splitlines() if not l.startswith("#")]
+        assert lines and all(l.split()[5] == h5_rel for l in lines)
+    # and our own reader of reference-written files goes through the same layout
+    one = next(iter(recs))
+    got = predetail.read_detail_hdf5(os.path.join(out_dir, h5_rel), one)
+    assert np.array_equal(got[2], recs[one][1]["refbasei"].astype(np.int64)) and got[4] == recs[one][0]["mapped_chr"]
