@@ -255,3 +255,69 @@ def test_converted_detail_is_read_by_the_unmodified_read_pred_detail(packed, tmp
     one = next(iter(recs))
     got = predetail.read_detail_hdf5(os.path.join(out_dir, h5_rel), one)
     assert np.array_equal(got[2], recs[one][1]["refbasei"].astype(np.int64)) and got[4] == recs[one][0]["mapped_chr"]
+
+
+class _OneJobQueue(object):
+    """What sum_handler needs of its multiprocessing queue (myDetect.py:1029-1034)."""
+
+    def __init__(self, job):
+        self.jobs = [job]
+
+    def empty(self):
+        return not self.jobs
+
+    def get(self, block=False):
+        return self.jobs.pop(0)
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted")
+def test_unmodified_sum_handler_summarises_our_detail_output(packed, tmp_path, monkeypatch):
+    """The whole --predDet 0 chain of the REFERENCE (sum_handler, :1028-1120: read_file_list -> read_pred_detail -> the
+    per-position dict -> BED text) run, unmodified, over OUR index files and converted detail records gives the BED text
+    the oracle derives directly from the predictions -- the same text the GPU path is held to."""
+    import sys
+    import types
+    batch, pb, pred, status = packed
+    names = ["chrA", "chrB"]
+    out_dir = str(tmp_path / "o" / "mod")
+    wrk = str(tmp_path / "in")
+    os.makedirs(wrk)
+    w = predetail.DetailWriter(out_dir, wrk, rank=0, contig_len=[30000, 12000])
+    w.add_batch(os.path.join(wrk, "b.dmreads.npz"), np.arange(pb.n_reads), pb, pred, status, names)
+    merged = predetail.merge_index_files(out_dir, wrk)
+    md = ref_harness.import_myDetect()
+    fake = types.ModuleType("h5py")
+    fake.File = _FakeFile
+    _FakeFile.store = {}
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    monkeypatch.setattr(md, "h5py", fake, raising=False)
+    if not hasattr(np, "int"):
+        monkeypatch.setattr(np, "int", int, raising=False)
+    predetail.convert_run(out_dir)
+    # the oracle's dict straight from the predictions (myDetect.py:1089-1100)
+    acc = {}
+    mod = predetail.column_predictions(pb, pred, status)
+    for r in np.flatnonzero(status == capi.READ_OK):
+        rd = detect_ref.unpack_read(batch, r)
+        c0 = int(batch["col_off"][r])
+        detect_ref.reduce_read(acc, names[rd["contig"]], rd["strand"], "C", rd["refbase"], rd["readbase"], rd["refpos"],
+                               mod[c0:c0 + len(rd["refbase"])])
+    want = detect_ref.bed_by_contig_strand(acc)
+    bed_dir = str(tmp_path / "beds")
+    os.makedirs(bed_dir)
+    devnull = open(os.devnull, "w")
+    monkeypatch.setattr(sys, "stdout", devnull)
+    try:
+        for path, chrom in zip(merged, names):
+            for strand in "+-":
+                md.sum_handler({"Base": "C", "mod_cluster": 0, "outFolder": bed_dir}, _OneJobQueue((path, chrom, strand)))
+    finally:
+        monkeypatch.undo()
+        devnull.close()
+    got = {}
+    for chrom in names:
+        for strand in "+-":
+            p = os.path.join(bed_dir, "mod_pos.%s%s.C.bed" % (chrom, strand))
+            if os.path.isfile(p):
+                got[(chrom, strand)] = open(p).read()
+    assert got == want and len(got) == 4 and sum(len(t) for t in got.values()) > 10000
