@@ -275,3 +275,43 @@ def test_stored_npz_reader_equals_numpy_and_falls_back(batch, tmp_path):
         fh.write(raw[:len(raw) // 3])
     with pytest.raises(Exception):
         reads_io.load_reads(t)
+
+
+@pytest.mark.parametrize("extra", [
+    [],
+    ["--region", "chr1:5:900;chr2", "--threads", "0", "--files_per_thread", "1", "--recursive", "0"],
+    ["--Base", "A", "--windowsize", "21", "--alignStr", "bwa", "--SignalGroup", "rundif", "--move", "--outLevel", "1"],
+])
+def test_option_assembly_equals_the_unmodified_reference_cli(tmp_path, monkeypatch, extra):
+    """The reference's own command line (bin/DeepMod.py, run unmodified with its manager captured) and ours assemble
+    the same ``moptions`` from the same ``detect`` argv: flag names, defaults, clamping, region parsing (:48-160, :309-338)."""
+    import runpy
+    import sys
+    from oracle import ref_harness
+    if not ref_harness.available():
+        pytest.skip("reference tree not mounted")
+    md = ref_harness.import_myDetect()                     # tensorflow / h5py stubbed, DeepMod_scripts importable
+    ref_fa = tmp_path / "ref.fa"
+    ref_fa.write_text(">c\nACGT\n")
+    mod = tmp_path / "m"
+    (tmp_path / "m.meta").write_text("")
+    argv = ["detect", "--wrkBase", str(tmp_path / "in") + "/", "--Ref", str(ref_fa), "--modfile", str(mod), "--FileID", "run7",
+            "--outFolder", str(tmp_path / "out")] + extra
+    seen = {}
+    monkeypatch.setattr(md, "mDetect_manager", lambda mo: seen.update(mo))
+    monkeypatch.setattr(sys, "argv", ["DeepMod.py"] + argv)
+    devnull = open(os.devnull, "w")
+    monkeypatch.setattr(sys, "stdout", devnull)
+    try:
+        runpy.run_path(os.path.join(ref_harness.REFERENCE_ROOT, "bin", "DeepMod.py"), run_name="__main__")
+    finally:
+        monkeypatch.undo()
+        devnull.close()
+    assert seen, "the reference CLI did not reach its manager"
+    args = cli.build_parser().parse_args(argv)
+    ours, err = cli.options_from_args(args)
+    assert err == ""
+    assert set(seen) <= set(ours), set(seen) - set(ours)          # every option the reference passes on exists here
+    for k in seen:
+        assert ours[k] == seen[k], (k, ours[k], seen[k])
+    assert set(ours) - set(seen) == {"precision", "saveDetail"}   # what this implementation adds
