@@ -54,3 +54,39 @@ def test_reference_script_runs_under_the_harness(tmp_path):
             fh.write("%s\t%d\t%s\n" % (c, p, s))
     cr.run_reference_script(w, str(tmp_path / "m"), str(tmp_path / "motif"))
     assert open(tmp_path / ("m_clusterCpG.%s.C.bed" % chrom)).read() == str(z["cluster_" + chrom])
+
+
+def test_motif_sites_equal_the_unmodified_generate_motif_pos(tmp_path):
+    """The CpG site list the cluster pass is fed (cluster.motif_sites_from_sequence) against the reference's own
+    generate_motif_pos.py, run unmodified as the script it is (DeepMod_tools/generate_motif_pos.py:56-71)."""
+    import os
+    import subprocess
+    import sys
+    import numpy as np
+    from deepmod_b200 import cluster, synth
+    from oracle import ref_harness
+    script = os.path.join(ref_harness.REFERENCE_ROOT, "DeepMod_tools", "generate_motif_pos.py")
+    if not os.path.isfile(script):
+        pytest.skip("reference tree not mounted")
+    genome = synth.make_genome([3000, 1700], seed=9)
+    genome[1][:2] = np.frombuffer(b"CG", np.uint8)                  # a site at the very start
+    genome[1][-2:] = np.frombuffer(b"CG", np.uint8)                 # and one at the very end
+    genome[0][-1] = ord("C")                                        # a trailing C without its G is not a site
+    fa = tmp_path / "ref.fa"
+    with open(fa, "w") as fh:
+        for name, g in zip(("chr1", "chr2"), genome):
+            s = g.tobytes().decode()
+            fh.write(">%s some description\n" % name)
+            for i in range(0, len(s), 60):
+                fh.write((s[i:i + 60].lower() if i % 120 == 0 else s[i:i + 60]) + "\n")      # the script upper-cases
+    out = tmp_path / "motif"
+    r = subprocess.run([sys.executable, script, str(fa), str(out), "C", "CG", "0", "1,2"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name, g in zip(("chr1", "chr2"), genome):
+        want = [(int(f[1]), f[2]) for f in (l.split() for l in open(out / ("motif_%s_C.bed" % name))) if len(f) == 3]
+        pos, strand = cluster.motif_sites_from_sequence(g)
+        got = sorted(zip(pos.tolist(), ["+" if s > 0 else "-" for s in strand]))
+        assert got == sorted(want) and len(got) > 50
+        # and the file reader the cluster CLI uses gives the same sites back
+        fp, fs = cluster.read_motif_file(str(out / ("motif_%s_C.bed" % name)))
+        assert sorted(zip(fp.tolist(), fs.tolist())) == sorted(zip(pos.tolist(), strand.tolist()))
