@@ -1,25 +1,27 @@
-// bf16 tensor-core path of the BiLSTM (tcgen05 / TMEM / bulk-TMA), sm_100a only.
+// Tensor-core path of the BiLSTM (tcgen05 / TMEM / bulk-TMA; fp16 or bf16 operands, fp32 accumulation), sm_100a only.
 //
 // Same graph as dm_lstm_fp32.cu (bin/DeepMod_scripts/myMultiBiRNN.py:30-61, 66 live
 // cell-steps), restructured for the B200:
 //
 //  * one CTA owns 128 windows (= the 128 TMEM lanes / UMMA M) for both directions;
 //  * every cell-step is ONE logical GEMM  gates[128,400] = A[128,K] * W[K,400]  issued as
-//    5 N-chunks of 80 gate columns (20 units x {i,j,f,o}) into a 6-slot TMEM ring, so the
-//    tensor pipe fills slot c+1.. while the epilogue warps drain slot c;
-//  * A is never materialised per step: it is the concatenation of the resident bf16 hidden
+//    5 N-chunks of 80 gate columns (20 units x {i,j,f,o}) into a TMEM ring of 5 slots (one per
+//    chunk: static addresses in the unrolled chunk loops), so the tensor pipe fills the slots of
+//    the next cell-step while the epilogue warps drain those of this one;
+//  * A is never materialised per step: it is the concatenation of the resident 16-bit hidden
 //    tiles (K-major core-matrix columns of 128 rows x 16 B).  Each hidden tile carries 4
-//    extra K slots (1, 1, mean_lo, stdv_lo): the bias rides in the GEMM as a bf16 hi/lo
+//    extra K slots (1, 1, mean_lo, stdv_lo): the bias rides in the GEMM as a hi/lo
 //    pair against the constant ones, the signal features as hi/lo pairs;
 //  * the three layers are walked in wavefront order (t+l = const), which makes consecutive
 //    cell-steps independent: MMA of step g+1 overlaps the epilogue of step g.  h0/h1 are
 //    double-buffered on the parity of t for that;
-//  * weights (bf16, 0.5 folded into the sigmoid gates, forget bias folded into the bias)
-//    stream from L2 through a 4-stage shared-memory ring with cp.async.bulk + mbarriers,
+//  * weights (0.5 folded into the sigmoid gates and into every row against a hidden state, forget
+//    bias folded into the bias) stream from L2 through a 5-stage shared-memory ring with cp.async.bulk + mbarriers,
 //    pre-arranged on the host in the exact UMMA canonical (no-swizzle, K-major) layout;
 //  * the epilogue (20 warps) reads 16 TMEM columns = 4 units per thread and chunk, packs the gate
 //    pre-activations of TWO units into f16x2 and applies sigmoid(x) = 0.5*tanh(x/2)+0.5 and tanh
-//    with ONE tanh.approx.f16x2 per pair (2.5 MUFU per unit instead of 5), does the cell update in
+//    with one tanh.approx.f16x2 per pair (which is still two MUFU.TANH.F16 in SASS: the MUFU pipe retires
+//    16.5 results per clock and SM whatever the format, and it is what binds this kernel), does the cell update in
 //    packed half2 FMAs (cell state in packed fp16 registers) and writes 2h straight into the next
 //    A operand (the factor 0.5 of h = 0.5*(tanh(c)*tanh(o/2) + tanh(c)) is folded into the weights);
 //  * operands are fp16 (DM_F16: h needs no conversion at all) or bf16 (DM_BF16), fp32 accumulate.
